@@ -1,0 +1,126 @@
+// vitssl_b200 — runtime glue of the C-ABI: error slot, launch accounting, device check and
+// host-side TMA descriptor encoding (driver entry point resolved at run time, so the library
+// links against cudart only).
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "vitssl_b200.h"
+
+namespace vitssl {
+
+static thread_local char g_error[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  ++g_launches;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(err));
+    return VITSSL_ERR_CUDA;
+  }
+  return VITSSL_OK;
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer) {
+  auto fn = encode_fn();
+  VITSSL_REQUIRE(fn != nullptr, VITSSL_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VITSSL_REQUIRE(r == CUDA_SUCCESS, VITSSL_ERR_CUDA,
+                 "cuTensorMapEncodeTiled(2d) failed: %d (inner %llu outer %llu pitch %llu box %u x %u)",
+                 (int)r, (unsigned long long)inner, (unsigned long long)outer,
+                 (unsigned long long)ld_bytes, box_inner, box_outer);
+  return VITSSL_OK;
+}
+
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2,
+                      uint64_t ld1_bytes, uint64_t ld2_bytes, uint32_t box_inner, uint32_t box_d1,
+                      uint32_t box_d2) {
+  auto fn = encode_fn();
+  VITSSL_REQUIRE(fn != nullptr, VITSSL_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {inner, d1, d2};
+  cuuint64_t strides[2] = {ld1_bytes, ld2_bytes};
+  cuuint32_t box[3] = {box_inner, box_d1, box_d2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VITSSL_REQUIRE(r == CUDA_SUCCESS, VITSSL_ERR_CUDA,
+                 "cuTensorMapEncodeTiled(3d) failed: %d (dims %llu %llu %llu pitches %llu %llu)",
+                 (int)r, (unsigned long long)inner, (unsigned long long)d1, (unsigned long long)d2,
+                 (unsigned long long)ld1_bytes, (unsigned long long)ld2_bytes);
+  return VITSSL_OK;
+}
+
+}  // namespace vitssl
+
+extern "C" int vitssl_version(void) { return 100; /* 0.1.0 */ }
+
+extern "C" const char* vitssl_last_error(void) { return vitssl::g_error; }
+
+extern "C" int vitssl_num_sms(void) { return vitssl::num_sms(); }
+
+extern "C" int64_t vitssl_launch_count(int reset) {
+  const long long v = vitssl::g_launches;
+  if (reset) vitssl::g_launches = 0;
+  return v;
+}
+
+extern "C" int vitssl_device_check(void) {
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) {
+    vitssl::set_error("no CUDA device: %s", cudaGetErrorString(err));
+    return VITSSL_ERR_DEVICE;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    vitssl::set_error("device %d is sm_%d%d; this library contains sm_100a code only", dev, major,
+                      minor);
+    return VITSSL_ERR_DEVICE;
+  }
+  return 0;
+}

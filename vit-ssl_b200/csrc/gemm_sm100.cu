@@ -1,0 +1,532 @@
+// vitssl_b200 — bf16 GEMM for sm_100a: TMA -> shared-memory ring -> tcgen05.mma -> TMEM ->
+// fused epilogue. One persistent, warp-specialised kernel serves every linear layer on the
+// hot path (reference call sites: attention.py:82-84,105; feed_forward.py:26-28;
+// patch_embedding.py:22,79-84,113-116; ssl/simmim/model.py:45,57; ssl/dino/head.py:10-17):
+//   forward   C[M,N]  = A[M,K] * W[N,K]^T      (both operands K-major)
+//   dgrad     dX[M,K] = dY[M,N] * W[N,K]       (B operand MN-major)
+//   wgrad     dW[N,K] = dY[M,N]^T * X[M,K]     (both operands MN-major, split-K + fp32 red)
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner,
+// warps 2-5 = epilogue (one TMEM lane quadrant each). Accumulators are double-buffered in
+// TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "vitssl_b200.h"
+
+namespace vitssl {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 192;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+struct GemmShape {
+  int M, N, K;
+  int m_tiles, n_tiles, splits;
+  int kblocks_total, kblocks_per_split;
+};
+
+struct GemmEpi {
+  void* c;
+  long long ldc;
+  const float* bias;
+  __nv_bfloat16* aux;
+  long long ld_aux;
+  float alpha;
+  int mode;      // VITSSL_EPI_*
+  int out_fp32;  // 1: fp32 output, 0: bf16
+  int atomic;    // 1: red.add.f32 into C (split-K)
+  int vec_ok;    // C / aux rows are 16-byte aligned -> vector stores
+  uint32_t drop_thresh16;
+  float drop_scale;
+  unsigned long long seed, offset;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 5 : (BN == 128) ? 6 : 8;
+  static constexpr int kBBytes = BN * BLOCK_K * 2;
+  static constexpr int kStageBytes = A_TILE_BYTES + kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// Abramowitz-Stegun 7.1.26 erfc core: for z >= 0, erfc(z) = poly(t) * exp(-z^2), |err| < 1.5e-7.
+// Returns the standard normal cdf Phi(x) = 0.5 * erfc(-x / sqrt(2)) and w = exp(-x^2 / 2).
+__device__ __forceinline__ float normal_cdf_fast(float x, float& w) {
+  const float az = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  w = __expf(-az * az);
+  const float half_erfc = 0.5f * poly * w;
+  return x < 0.0f ? half_erfc : 1.0f - half_erfc;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmShape s,
+                    const GemmEpi e) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int STAGE_BYTES = Cfg::kStageBytes;
+  constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BN, A_MN, B_MN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_work = s.m_tiles * s.n_tiles * s.splits;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int n_blk = w % s.n_tiles;
+        const int m_blk = (w / s.n_tiles) % s.m_tiles;
+        const int sp = w / (s.n_tiles * s.m_tiles);
+        const int kb0 = sp * s.kblocks_per_split;
+        const int kb1 = min(kb0 + s.kblocks_per_split, s.kblocks_total);
+        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* a_dst = smem + stage * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_TILE_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d(a_dst, &tmap_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(a_dst + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(b_dst, &tmap_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b_dst + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int sp = w / (s.n_tiles * s.m_tiles);
+        const int kb0 = sp * s.kblocks_per_split;
+        const int kb1 = min(kb0 + s.kblocks_per_split, s.kblocks_total);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // K-major: 16 bf16 = 32 bytes along the swizzled row; 8-row groups 1024 B apart.
+            // MN-major: 16 k-rows = 2048 bytes; 64-wide MN groups 8192 B apart (LBO),
+            //           8-row k groups 1024 B apart (SBO).
+            const uint64_t da = A_MN ? umma_desc_sw128(a_base + k * 2048, 8192, 1024)
+                                     : umma_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc_sw128(b_base + k * 2048, 8192, 1024)
+                                     : umma_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_bf16_ss(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int n_blk = w % s.n_tiles;
+      const int m_blk = (w / s.n_tiles) % s.m_tiles;
+      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {  // accumulator drained into registers: hand TMEM back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        const int nb = n0 + c * 32;
+        if (row >= s.M || nb >= s.N) continue;
+        const int ncols = min(32, s.N - nb);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * e.alpha;
+
+        if (e.mode == VITSSL_EPI_BIAS || e.mode == VITSSL_EPI_BIAS_GELU) {
+          if (ncols == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + nb + i));
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+          } else {
+            _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(e.bias + nb + i);
+          }
+        }
+        uint32_t keep = 0xffffffffu;
+        if (e.drop_thresh16 != 0 &&
+            (e.mode == VITSSL_EPI_BIAS_GELU || e.mode == VITSSL_EPI_DGELU)) {
+          const unsigned long long g8 =
+              (static_cast<unsigned long long>(row) * s.N + nb) >> 3;  // N % 8 == 0 enforced
+          keep = 0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            keep |= dropout_keep8(e.seed, e.offset, g8 + g, e.drop_thresh16) << (8 * g);
+        }
+        if (e.mode == VITSSL_EPI_BIAS_GELU) {
+          // u = bf16(acc + b) is saved for backward; h = dropout(gelu(u))
+          __nv_bfloat16* ap = e.aux + static_cast<long long>(row) * e.ld_aux + nb;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+          if (ncols == 32 && e.vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 pk;
+              pk.x = pack_bf16(v[i], v[i + 1]); pk.y = pack_bf16(v[i + 2], v[i + 3]);
+              pk.z = pack_bf16(v[i + 4], v[i + 5]); pk.w = pack_bf16(v[i + 6], v[i + 7]);
+              *reinterpret_cast<uint4*>(ap + i) = pk;
+            }
+          } else {
+            _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) ap[i] = __float2bfloat16_rn(v[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float wgt;
+            const float cdf = normal_cdf_fast(v[i], wgt);
+            float h = v[i] * cdf;
+            h = ((keep >> i) & 1u) ? h * e.drop_scale : 0.0f;
+            v[i] = h;
+          }
+        } else if (e.mode == VITSSL_EPI_DGELU) {
+          // dU = dH * dropout_mask/(1-p) * gelu'(u), u read back from the forward's aux
+          const __nv_bfloat16* ap = e.aux + static_cast<long long>(row) * e.ld_aux + nb;
+          float u[32];
+          if (ncols == 32 && e.vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(ap + i);
+              u[i] = bf16_lo(pk.x); u[i + 1] = bf16_hi(pk.x);
+              u[i + 2] = bf16_lo(pk.y); u[i + 3] = bf16_hi(pk.y);
+              u[i + 4] = bf16_lo(pk.z); u[i + 5] = bf16_hi(pk.z);
+              u[i + 6] = bf16_lo(pk.w); u[i + 7] = bf16_hi(pk.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = (i < ncols) ? __bfloat162float(ap[i]) : 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float wgt;
+            const float cdf = normal_cdf_fast(u[i], wgt);
+            const float g = fmaf(u[i] * 0.3989422804014327f, wgt, cdf);
+            v[i] = ((keep >> i) & 1u) ? v[i] * g * e.drop_scale : 0.0f;
+          }
+        }
+
+        if (e.atomic) {
+          float* cp = reinterpret_cast<float*>(e.c) + static_cast<long long>(row) * e.ldc + nb;
+          _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) atomicAdd(cp + i, v[i]);
+        } else if (e.out_fp32) {
+          float* cp = reinterpret_cast<float*>(e.c) + static_cast<long long>(row) * e.ldc + nb;
+          if (ncols == 32 && e.vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) cp[i] = v[i];
+          }
+        } else {
+          __nv_bfloat16* cp =
+              reinterpret_cast<__nv_bfloat16*>(e.c) + static_cast<long long>(row) * e.ldc + nb;
+          if (ncols == 32 && e.vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 pk;
+              pk.x = pack_bf16(v[i], v[i + 1]); pk.y = pack_bf16(v[i + 2], v[i + 3]);
+              pk.z = pack_bf16(v[i + 4], v[i + 5]); pk.w = pack_bf16(v[i + 6], v[i + 7]);
+              *reinterpret_cast<uint4*>(cp + i) = pk;
+            }
+          } else {
+            _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) cp[i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// Generic SIMT GEMM for shapes TMA cannot address (row pitch not a multiple of 16 bytes, e.g.
+// the 10-class MLP head, mlp_head.py:10). 32x32 tiles, fp32 accumulate. Tiny problems only.
+// ----------------------------------------------------------------------------------
+__global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A,
+                                 const __nv_bfloat16* __restrict__ B, int M, int N, int K,
+                                 long long lda, long long ldb, int a_mn, int b_mn,
+                                 const GemmEpi e) {
+  __shared__ float As[32][33];
+  __shared__ float Bs[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int i = ty; i < 32; i += 8) {
+      // As[i][tx] = A(m0+i, k0+tx); Bs[i][tx] = B(k0+tx, n0+i)
+      float av = 0.f, bv = 0.f;
+      if (a_mn) {  // A stored [K][M]: read with M fastest
+        const int m = m0 + tx, k = k0 + i;
+        if (m < M && k < K) av = __bfloat162float(A[static_cast<long long>(k) * lda + m]);
+        As[tx][i] = av;
+      } else {
+        const int m = m0 + i, k = k0 + tx;
+        if (m < M && k < K) av = __bfloat162float(A[static_cast<long long>(m) * lda + k]);
+        As[i][tx] = av;
+      }
+      if (b_mn) {  // B stored [K][N]
+        const int n = n0 + tx, k = k0 + i;
+        if (n < N && k < K) bv = __bfloat162float(B[static_cast<long long>(k) * ldb + n]);
+        Bs[tx][i] = bv;
+      } else {  // B stored [N][K]
+        const int n = n0 + i, k = k0 + tx;
+        if (n < N && k < K) bv = __bfloat162float(B[static_cast<long long>(n) * ldb + k]);
+        Bs[i][tx] = bv;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float b = Bs[tx][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(As[ty + 8 * j][k], b, acc[j]);
+    }
+    __syncthreads();
+  }
+  const int n = n0 + tx;
+  if (n >= N) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int m = m0 + ty + 8 * j;
+    if (m >= M) continue;
+    float v = acc[j] * e.alpha;
+    if (e.mode == VITSSL_EPI_BIAS || e.mode == VITSSL_EPI_BIAS_GELU) v += e.bias[n];
+    if (e.mode == VITSSL_EPI_BIAS_GELU) {
+      v = bf16_round(v);
+      e.aux[static_cast<long long>(m) * e.ld_aux + n] = __float2bfloat16_rn(v);
+      v = gelu_erf(v);
+    } else if (e.mode == VITSSL_EPI_DGELU) {
+      v *= gelu_erf_grad(__bfloat162float(e.aux[static_cast<long long>(m) * e.ld_aux + n]));
+    }
+    if (e.out_fp32)
+      reinterpret_cast<float*>(e.c)[static_cast<long long>(m) * e.ldc + n] = v;
+    else
+      reinterpret_cast<__nv_bfloat16*>(e.c)[static_cast<long long>(m) * e.ldc + n] =
+          __float2bfloat16_rn(v);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s,
+                   const GemmEpi& e, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t err =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (err != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
+      return VITSSL_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int num_work = s.m_tiles * s.n_tiles * s.splits;
+  const int grid = num_work < num_sms() ? num_work : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, s, e);
+  return check_launch("gemm_tcgen05");
+}
+
+template <bool A_MN, bool B_MN>
+int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s,
+                const GemmEpi& e, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch_tcgen05<64, A_MN, B_MN>(ta, tb, s, e, stream);
+    case 128: return launch_tcgen05<128, A_MN, B_MN>(ta, tb, s, e, stream);
+    case 192: return launch_tcgen05<192, A_MN, B_MN>(ta, tb, s, e, stream);
+    default: return launch_tcgen05<256, A_MN, B_MN>(ta, tb, s, e, stream);
+  }
+}
+
+int pick_block_n(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 128 == 0) return 128;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  if (N <= 192) return 192;
+  return 256;
+}
+
+}  // namespace
+
+}  // namespace vitssl
+
+using namespace vitssl;
+
+extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N,
+                                int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn,
+                                int b_mn, int epilogue, const float* bias, void* aux,
+                                int64_t ld_aux, float alpha, int out_fp32, int split_k,
+                                float dropout_p, uint64_t philox_seed, uint64_t philox_offset,
+                                cudaStream_t stream) {
+  VITSSL_REQUIRE(A && B && C, VITSSL_ERR_ARG, "gemm: null operand");
+  VITSSL_REQUIRE(M > 0 && N > 0 && K > 0, VITSSL_ERR_SHAPE, "gemm: empty problem %lld x %lld x %lld",
+                 (long long)M, (long long)N, (long long)K);
+  VITSSL_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), VITSSL_ERR_SHAPE,
+                 "gemm: dimension exceeds int32");
+  VITSSL_REQUIRE(epilogue >= VITSSL_EPI_NONE && epilogue <= VITSSL_EPI_DGELU, VITSSL_ERR_ARG,
+                 "gemm: bad epilogue %d", epilogue);
+  if (epilogue == VITSSL_EPI_BIAS || epilogue == VITSSL_EPI_BIAS_GELU)
+    VITSSL_REQUIRE(bias != nullptr, VITSSL_ERR_ARG, "gemm: epilogue needs bias");
+  if (epilogue == VITSSL_EPI_BIAS_GELU || epilogue == VITSSL_EPI_DGELU)
+    VITSSL_REQUIRE(aux != nullptr && ld_aux >= N, VITSSL_ERR_ARG, "gemm: epilogue needs aux");
+  VITSSL_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, VITSSL_ERR_ARG, "gemm: dropout_p out of range");
+  if (dropout_p > 0.f)
+    VITSSL_REQUIRE(N % 8 == 0, VITSSL_ERR_SHAPE, "gemm: dropout epilogue needs N %% 8 == 0");
+
+  GemmEpi e{};
+  e.c = C; e.ldc = ldc; e.bias = bias; e.aux = reinterpret_cast<__nv_bfloat16*>(aux);
+  e.ld_aux = ld_aux; e.alpha = alpha; e.mode = epilogue; e.out_fp32 = out_fp32;
+  e.drop_thresh16 = static_cast<uint32_t>(dropout_p * 65536.0f);
+  e.drop_scale = 1.0f / (1.0f - dropout_p);
+  e.seed = philox_seed; e.offset = philox_offset;
+
+  // TMA needs 16-byte aligned bases and row pitches
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(B) % 16 == 0) && (lda % 8 == 0) &&
+                      (ldb % 8 == 0);
+  if (!tma_ok) {
+    VITSSL_REQUIRE(dropout_p == 0.f, VITSSL_ERR_SHAPE, "gemm: dropout unsupported on unaligned path");
+    e.atomic = 0; e.vec_ok = 0;
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + 31) / 32));
+    gemm_simt_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A),
+                                               reinterpret_cast<const __nv_bfloat16*>(B), (int)M,
+                                               (int)N, (int)K, lda, ldb, a_mn, b_mn, e);
+    return check_launch("gemm_simt");
+  }
+
+  const int bn = pick_block_n((int)N);
+  GemmShape s{};
+  s.M = (int)M; s.N = (int)N; s.K = (int)K;
+  s.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  s.n_tiles = (int)((N + bn - 1) / bn);
+  s.kblocks_total = (int)((K + BLOCK_K - 1) / BLOCK_K);
+  int splits = 1;
+  if (split_k != 0 && out_fp32 && epilogue == VITSSL_EPI_NONE) {
+    if (split_k > 0) {
+      splits = split_k;
+    } else {  // auto: fill the machine, keep >= 4 k-blocks per split
+      const int tiles = s.m_tiles * s.n_tiles;
+      splits = (num_sms() + tiles - 1) / tiles;
+      const int max_splits = s.kblocks_total / 4 > 0 ? s.kblocks_total / 4 : 1;
+      if (splits > max_splits) splits = max_splits;
+    }
+    if (splits < 1) splits = 1;
+    if (splits > s.kblocks_total) splits = s.kblocks_total;
+  }
+  s.kblocks_per_split = (s.kblocks_total + splits - 1) / splits;
+  s.splits = (s.kblocks_total + s.kblocks_per_split - 1) / s.kblocks_per_split;
+  e.atomic = s.splits > 1 ? 1 : 0;
+  const int elt = out_fp32 ? 4 : 2;
+  e.vec_ok = (reinterpret_cast<uintptr_t>(C) % 16 == 0) && ((ldc * elt) % 16 == 0);
+  if (aux) e.vec_ok = e.vec_ok && (reinterpret_cast<uintptr_t>(aux) % 16 == 0) && (ld_aux % 8 == 0);
+  if (e.atomic) {
+    cudaError_t err = cudaMemset2DAsync(C, ldc * 4, 0, N * 4, M, stream);
+    if (err != cudaSuccess) {
+      set_error("gemm: memset failed: %s", cudaGetErrorString(err));
+      return VITSSL_ERR_CUDA;
+    }
+  }
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, BLOCK_M);
+  else       rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, 64);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, bn);
+  else       rc = make_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64);
+  if (rc) return rc;
+
+  if (!a_mn && !b_mn) return dispatch_bn<false, false>(bn, ta, tb, s, e, stream);
+  if (!a_mn && b_mn) return dispatch_bn<false, true>(bn, ta, tb, s, e, stream);
+  if (a_mn && b_mn) return dispatch_bn<true, true>(bn, ta, tb, s, e, stream);
+  return dispatch_bn<true, false>(bn, ta, tb, s, e, stream);
+}

@@ -1,0 +1,102 @@
+"""ctypes binding of `libvitssl_b200.so` (C ABI declared in `include/vitssl_b200.h`).
+
+There is no CPU fallback: if the library is missing or the device is not sm_100, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))  # .../vit-ssl_b200
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libvitssl_b200.so")
+
+_T = {
+    "p": ctypes.c_void_p,
+    "i": ctypes.c_int,
+    "l": ctypes.c_int64,
+    "f": ctypes.c_float,
+    "u": ctypes.c_uint64,
+    "s": ctypes.c_void_p,  # cudaStream_t
+}
+
+# name -> argument signature (one letter per argument, see _T). Must mirror include/vitssl_b200.h.
+SIGNATURES = {}
+# the gemm signature spelled out (A,B,C | M,N,K,lda,ldb,ldc | a_mn,b_mn,epilogue | bias,aux |
+# ld_aux | alpha | out_fp32, split_k | dropout_p | seed, offset | stream)
+SIGNATURES["vitssl_gemm_bf16"] = "ppp" + "llllll" + "iii" + "pp" + "l" + "f" + "ii" + "f" + "uu" + "s"
+
+_lib = None
+
+
+class VitsslError(RuntimeError):
+    pass
+
+
+def _load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"vitssl_b200: native library not found at {LIB_PATH}; build it with "
+            f"`python {os.path.join(_PKG_ROOT, 'build.py')}` (there is no CPU fallback)."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.vitssl_version.restype = ctypes.c_int
+    lib.vitssl_last_error.restype = ctypes.c_char_p
+    lib.vitssl_device_check.restype = ctypes.c_int
+    lib.vitssl_num_sms.restype = ctypes.c_int
+    lib.vitssl_launch_count.restype = ctypes.c_int64
+    lib.vitssl_launch_count.argtypes = [ctypes.c_int]
+    for name, sig in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [_T[c] for c in sig]
+    _lib = lib
+    return lib
+
+
+def lib():
+    return _load()
+
+
+_device_ok = False
+
+
+def ensure_device():
+    """Raise unless the current CUDA device can run the sm_100a kernels."""
+    global _device_ok
+    if _device_ok:
+        return
+    if not torch.cuda.is_available():
+        raise VitsslError("vitssl_b200 needs a CUDA device (sm_100a / B200); no CPU fallback exists")
+    l = _load()
+    rc = l.vitssl_device_check()
+    if rc != 0:
+        raise VitsslError(l.vitssl_last_error().decode())
+    _device_ok = True
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def call(name: str, *args):
+    l = _load()
+    rc = getattr(l, name)(*args)
+    if rc != 0:
+        raise VitsslError(f"{name} failed ({rc}): {l.vitssl_last_error().decode()}")
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(_load().vitssl_launch_count(1 if reset else 0))
