@@ -60,6 +60,124 @@ int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N
                      int split_k, float dropout_p, uint64_t philox_seed, uint64_t philox_offset,
                      vitssl_stream_t stream);
 
+/* ---- fused residual-add (+dropout) + LayerNorm ------------------------------------------
+ * encoder_block.py:40-52:  x_out = x + dropout(branch);  y = LayerNorm(x_out) (eps, affine).
+ *   x      fp32 rows of pitch ldx (elements);  branch bf16 dense [rows,D] or NULL (then x_out
+ *   must be NULL and the LayerNorm reads x);  gamma/beta NULL -> add only (y/mean/rstd unused).
+ *   y bf16 dense; mean/rstd fp32 [rows] are saved for backward. */
+int vitssl_add_layernorm_fwd(const float* x, int64_t ldx, const void* branch, float* x_out,
+                             const float* gamma, const float* beta, void* y, float* mean,
+                             float* rstd, int64_t rows, int64_t D, float eps, float dropout_p,
+                             uint64_t philox_seed, uint64_t philox_offset, vitssl_stream_t stream);
+/* backward of the above. dy (bf16, NULL for the add-only form) is the gradient of y; dres (fp32,
+ * nullable) the gradient arriving on the residual stream. Outputs: dx (fp32, total gradient of
+ * x_out, which is also the gradient of x) and dbranch (bf16, nullable) = dropout-mask * dx.
+ * dgamma/dbeta [D] are zeroed on `stream` and accumulated. */
+int vitssl_add_layernorm_bwd(const void* dy, const float* x, int64_t ldx, const float* mean,
+                             const float* rstd, const float* gamma, const float* dres,
+                             int64_t ld_dres, float* dx, int64_t ld_dx, void* dbranch,
+                             float* dgamma, float* dbeta, int64_t rows, int64_t D, float dropout_p,
+                             uint64_t philox_seed, uint64_t philox_offset, vitssl_stream_t stream);
+
+/* ---- multi-head attention (attention.py:5-27, 86-103) -----------------------------------
+ * q/k/v/out are bf16 [B, S, H, 64] views: token rows of pitch ld* elements, head h at column
+ * 64*h (so the fused QKV GEMM output is addressed in place). tcgen05 path: d_head = 64,
+ * Sk <= 256 (and Sq <= 256 for backward). lse fp32 [B,H,Sq] is saved by forward for backward. */
+int vitssl_attention_supported(int64_t Sq, int64_t Sk, int64_t d_head);
+int vitssl_attention_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
+                         int64_t ldv, void* out, int64_t ldo, float* lse, int64_t B, int64_t H,
+                         int64_t Sq, int64_t Sk, float scale, vitssl_stream_t stream);
+int vitssl_attention_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
+                         int64_t ldv, const void* out, const void* d_out, int64_t ldo,
+                         const float* lse, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
+                         int64_t lddv, int64_t B, int64_t H, int64_t Sq, int64_t Sk, float scale,
+                         vitssl_stream_t stream);
+/* generic SIMT attention: any head dim / length, explicit element strides
+ * host_strides[12] = {q_b,q_h,q_s, k_b,k_h,k_s, v_b,v_h,v_s, o_b,o_h,o_s}; probs (fp32
+ * [B,H,Sq,Sk]) and lse are optional outputs (return_attn=True path, attention.py:24-25).
+ * backward accumulates dK/dV into pre-zeroed fp32 [B,Sk,H,d] buffers. */
+int vitssl_attention_generic_fwd(const void* q, const void* k, const void* v,
+                                 const int64_t* host_strides, void* out, float* probs, float* lse,
+                                 int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t d,
+                                 float scale, vitssl_stream_t stream);
+int vitssl_attention_generic_bwd(const void* q, const void* k, const void* v,
+                                 const int64_t* host_strides, const void* out, const void* d_out,
+                                 const float* lse, void* dq, float* dk_acc, float* dv_acc,
+                                 int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t d,
+                                 float scale, vitssl_stream_t stream);
+
+/* ---- weight casts, EMA, bias gradients (host_* arguments are HOST arrays of device pointers) */
+/* fp32 -> bf16 for `count` tensors in one or a few launches (parameters stay fp32 nn.Parameters;
+ * the GEMMs read bf16 shadows, like autocast's per-call weight casts). */
+int vitssl_multi_cast_bf16(const void* const* host_src, void* const* host_dst,
+                           const int64_t* host_numel, int count, vitssl_stream_t stream);
+/* teacher <- m * teacher + (1 - m) * student over parameter lists (ssl/dino/model.py:126-139). */
+int vitssl_multi_ema(void* const* host_teacher, const void* const* host_student,
+                     const int64_t* host_numel, int count, float momentum, vitssl_stream_t stream);
+/* out[c] = sum_r x[r,c] (bf16 in, fp32 out; out is zeroed on `stream`): bias gradients. */
+int vitssl_colsum_bf16(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out,
+                       vitssl_stream_t stream);
+
+/* ---- patches and tokens ------------------------------------------------------------------ */
+/* img fp32 [B,C,H,W] -> bf16 [B*(H/p)*(W/p), C*p*p], feature order (c,ph,pw), patches row-major
+ * (nn.Unfold: ssl/simmim/model.py:43; Conv2d(k=s=p) im2col: patch_embedding.py:22,79-84). */
+int vitssl_im2col_bf16(const float* img, void* out, int64_t B, int64_t C, int64_t H, int64_t W,
+                       int64_t p, vitssl_stream_t stream);
+/* raw fp32 patches of the listed flat patch ids (b*N + n): SimMIM targets (masking.py:35). */
+int vitssl_gather_patches_f32(const float* img, const int32_t* rows_idx, float* out, int64_t n_rows,
+                              int64_t C, int64_t H, int64_t W, int64_t p, vitssl_stream_t stream);
+/* x[b,s,:] = (CLS | mask_token | proj[b,n,:]) + pos[s,:]   (patch_embedding.py:61-63,94-95;
+ * ssl/simmim/model.py:47-49). cls NULL -> no CLS row (S = N); mask (uint8 [B*N]) NULL -> none. */
+int vitssl_embed_tokens_fwd(const void* proj, const float* cls, const float* pos,
+                            const uint8_t* mask, const float* mask_token, float* x, int64_t B,
+                            int64_t N, int64_t D, vitssl_stream_t stream);
+/* backward: dproj (bf16, zero on masked rows), dpos [S,D] (row 0 is also d(cls) when has_cls),
+ * dmask_token [D] (nullable). dx is addressed with element strides (ld_b, ld_s). */
+int vitssl_embed_tokens_bwd(const float* dx, int64_t ld_b, int64_t ld_s, const uint8_t* mask,
+                            void* dproj, float* dpos, float* dmask_token, int64_t B, int64_t N,
+                            int64_t D, int has_cls, vitssl_stream_t stream);
+/* out[i,:] = bf16(x[idx[i],:]) — sync-free form of x[bool_mask] (ssl/simmim/model.py:56). */
+int vitssl_gather_rows_bf16(const float* x, int64_t ldx, const int32_t* idx, void* out,
+                            int64_t n_rows, int64_t D, vitssl_stream_t stream);
+/* its backward: dx[r,:] = inv_idx[r] >= 0 ? dy[inv_idx[r],:] : 0 for every row r. */
+int vitssl_scatter_rows_f32(const void* dy, const int32_t* inv_idx, float* dx, int64_t rows,
+                            int64_t D, vitssl_stream_t stream);
+
+/* ---- SimMIM objective --------------------------------------------------------------------- */
+/* loss[0] = mean |pred - target| (nn.L1Loss(mean): utils/train_utils.py:19-22); sign (bf16,
+ * nullable) receives sign(pred - target) so that d(pred) = sign * grad / n needs no second read
+ * of the targets. pred bf16, target fp32. */
+int vitssl_l1_loss_fwd(const void* pred, const float* target, void* sign, float* loss, int64_t n,
+                       vitssl_stream_t stream);
+
+/* ---- DINO objective ------------------------------------------------------------------------ */
+/* F.normalize(dim=1) (ssl/dino/head.py:21), bf16 rows. */
+int vitssl_l2norm_fwd(const void* x, void* y, float* inv_norm, int64_t rows, int64_t D,
+                      vitssl_stream_t stream);
+int vitssl_l2norm_bwd(const void* x, const float* inv_norm, const void* dy, void* dx, int64_t rows,
+                      int64_t D, vitssl_stream_t stream);
+/* weight_norm(Linear) (head.py:17): w = g * v / ||v||_row -> bf16; backward maps dW to (dg, dv). */
+int vitssl_weight_norm_fwd(const float* v, const float* g, void* w, float* inv_norm, int64_t rows,
+                           int64_t D, vitssl_stream_t stream);
+int vitssl_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm,
+                           float* dg, float* dv, int64_t rows, int64_t D, vitssl_stream_t stream);
+/* out = m * center + (1 - m) * colsum * inv_rows (ssl/dino/model.py:96-99); colsum comes from
+ * vitssl_colsum_bf16 over the teacher logits (all-reduced across ranks first under DP). */
+int vitssl_center_ema(const float* center, const float* colsum, float* out, int64_t K, float momentum,
+                      float inv_rows, vitssl_stream_t stream);
+/* DINOLoss (ssl/dino/loss.py:13-29) for teacher bf16 [G,B,K], student bf16 [V,B,K], center [K]:
+ * loss[0] = -(1/(G B K)) sum_b sum_k (sum_g softmax((T_g-c)/tt))(sum_v log_softmax(S_v/ts)).
+ * t_stats [G,B,2] and s_lse [V,B] are saved for backward. G <= 2, V <= 12, K % 8 == 0. */
+int vitssl_dino_loss_fwd(const void* teacher, const void* student, const float* center, float* loss,
+                         float* t_stats, float* s_lse, int64_t G, int64_t V, int64_t B, int64_t K,
+                         float teacher_temp, float student_temp, vitssl_stream_t stream);
+/* dstudent[v,b,k] = -(grad_out/(ts G B K)) (Pbar[b,k] - G softmax(S_v/ts)[k]); grad_out is a
+ * DEVICE scalar (the GradScaler-scaled upstream gradient) so no host sync is needed. */
+int vitssl_dino_loss_bwd(const void* teacher, const void* student, const float* center,
+                         const float* t_stats, const float* s_lse, const float* grad_out,
+                         void* dstudent, int64_t G, int64_t V, int64_t B, int64_t K,
+                         float teacher_temp, float student_temp, vitssl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

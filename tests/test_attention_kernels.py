@@ -1,0 +1,89 @@
+"""GPU parity of the attention kernels against the oracle's float64 attention
+(attention.py:5-27): tcgen05 forward/backward (d_k = 64, S <= 256) and the generic SIMT path."""
+import math
+
+import pytest
+import torch
+
+from oracle import vit_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from vit_core._backend import ops
+    return ops
+
+
+def _ref(qkv, B, S, H):
+    D = H * 64
+    q, k, v = [t.reshape(B, S, H, 64).transpose(1, 2) for t in qkv.double().split(D, dim=-1)]
+    q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+    ctx, probs = vit_ref.scaled_dot_product_attention(q, k, v)
+    return q, k, v, ctx, probs
+
+
+@pytest.mark.parametrize("B,S,H", [(2, 196, 6), (3, 197, 6), (2, 37, 3), (1, 256, 2), (2, 128, 1), (5, 16, 4), (2, 144, 6), (1, 1, 1), (2, 129, 2)])
+def test_attention_tcgen05_fwd_bwd(B, S, H):
+    ops = _ops()
+    D = H * 64
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    qkv = (torch.randn(B, S, 3 * D, generator=g)).to(torch.bfloat16)
+    d_out = (torch.randn(B, S, D, generator=g)).to(torch.bfloat16)
+    q, k, v, ctx_ref, _ = _ref(qkv, B, S, H)
+    (ctx_ref.transpose(1, 2).reshape(B, S, D) * d_out.double()).sum().backward()
+
+    qkv_c = qkv.cuda()
+    qv, kv, vv = qkv_c[..., :D], qkv_c[..., D:2 * D], qkv_c[..., 2 * D:]
+    scale = 1.0 / math.sqrt(64)
+    out, lse = ops.attention_fwd(qv, kv, vv, H, scale)
+    ref_ctx = ctx_ref.detach().transpose(1, 2).reshape(B, S, D)
+    err = (out.double().cpu() - ref_ctx).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref_ctx.abs().max().item()), err
+    # log-sum-exp of the scaled scores
+    scores = torch.matmul(q.detach(), k.detach().transpose(-2, -1)) * scale
+    assert torch.allclose(lse.double().cpu(), torch.logsumexp(scores, dim=-1), atol=1e-3)
+
+    dqkv = torch.empty_like(qkv_c)
+    ops.attention_bwd(qv, kv, vv, out, d_out.cuda(), lse, H, scale,
+                      dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:])
+    for name, got, ref in (("dq", dqkv[..., :D], q.grad), ("dk", dqkv[..., D:2 * D], k.grad), ("dv", dqkv[..., 2 * D:], v.grad)):
+        ref = ref.transpose(1, 2).reshape(B, S, D)
+        e = (got.double().cpu() - ref).abs().max().item()
+        assert e < 3e-2 * max(1e-3, ref.abs().max().item()), (name, e, ref.abs().max().item())
+
+
+def test_attention_cross_lengths_tcgen05():
+    ops = _ops()
+    B, Sq, Sk, H = 2, 70, 200, 2
+    D = H * 64
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(B, Sq, D, generator=g).to(torch.bfloat16)
+    k = torch.randn(B, Sk, D, generator=g).to(torch.bfloat16)
+    v = torch.randn(B, Sk, D, generator=g).to(torch.bfloat16)
+    qh, kh, vh = [t.double().reshape(B, -1, H, 64).transpose(1, 2) for t in (q, k, v)]
+    ref, _ = vit_ref.scaled_dot_product_attention(qh, kh, vh)
+    out, _ = ops.attention_fwd(q.cuda(), k.cuda(), v.cuda(), H, 0.125)
+    ref = ref.transpose(1, 2).reshape(B, Sq, D)
+    assert (out.double().cpu() - ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,d", [(4, 1, 10, 10, 10), (4, 8, 10, 12, 8), (2, 6, 300, 300, 64), (3, 4, 17, 17, 32)])
+def test_attention_generic_fwd_bwd(B, H, Sq, Sk, d):
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(B, H, Sq, d, generator=g).to(torch.bfloat16)
+    k = torch.randn(B, H, Sk, d, generator=g).to(torch.bfloat16)
+    v = torch.randn(B, H, Sk, d, generator=g).to(torch.bfloat16)
+    d_out = torch.randn(B, H, Sq, d, generator=g).to(torch.bfloat16)
+    qr, kr, vr = [t.double().requires_grad_(True) for t in (q, k, v)]
+    ref, probs_ref = vit_ref.scaled_dot_product_attention(qr, kr, vr)
+    (ref * d_out.double()).sum().backward()
+    scale = 1.0 / math.sqrt(d)
+    out, probs, lse = ops.attention_generic_fwd(q.cuda(), k.cuda(), v.cuda(), scale, want_probs=True)
+    assert (out.double().cpu() - ref.detach()).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert torch.allclose(probs.double().cpu(), probs_ref.detach(), atol=1e-5)
+    dq, dk, dv = ops.attention_generic_bwd(q.cuda(), k.cuda(), v.cuda(), out, d_out.cuda(), lse, scale)
+    assert (dq.double().cpu() - qr.grad).abs().max().item() < 3e-2 * qr.grad.abs().max().item()
+    assert (dk.double().cpu().transpose(1, 2) - kr.grad).abs().max().item() < 3e-2 * kr.grad.abs().max().item()
+    assert (dv.double().cpu().transpose(1, 2) - vr.grad).abs().max().item() < 3e-2 * vr.grad.abs().max().item()

@@ -1,0 +1,235 @@
+"""GPU parity of the drop-in `vit_core` modules against golden vectors produced by the real
+reference (float64, same weights, same inputs, dropout 0). Tolerances are the north-star ones:
+max relative error <= 1e-2 on activations and gradients (bf16 compute, fp32 accumulation),
+<= 1e-3 on losses; masks bit-exact."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vit_ref
+from oracle.cases import build_dino_case, digest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ACT_TOL, GRAD_TOL, LOSS_TOL = 1e-2, 1e-2, 1e-3
+
+
+def load(name):
+    return torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+
+
+def rel(a, b):
+    b = b.double().cpu()
+    return ((a.detach().double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def check_grads(module, golden_grads, tol=GRAD_TOL):
+    worst = ("", 0.0)
+    for k, p in module.named_parameters():
+        if k not in golden_grads:
+            continue
+        assert p.grad is not None, k
+        e = rel(p.grad, golden_grads[k])
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] <= tol, worst
+    return worst
+
+
+def test_encoder_block():
+    from vit_core import EncoderBlock
+    g = load("encoder_block")
+    m = EncoderBlock(d_model=128, num_heads=2, mlp_dim=256, dropout=0.0)
+    m.load_state_dict(g["weights"])
+    m.cuda()
+    x = g["x"].cuda().requires_grad_(True)
+    y, probs = m(x, return_attn=True)
+    assert y.dtype == torch.float32 and y.shape == g["y"].shape
+    assert rel(y, g["y"]) <= ACT_TOL
+    assert rel(probs, g["probs"]) <= ACT_TOL
+    (y * g["dy"].cuda()).sum().backward()
+    assert rel(x.grad, g["dx"]) <= GRAD_TOL
+    check_grads(m, g["grads"])
+    y2, none = m(g["x"].cuda())
+    assert none is None and torch.equal(y2, y)
+
+
+def test_mha_cross_attention():
+    from vit_core import MultiHeadedAttention
+    g = load("mha_cross")
+    m = MultiHeadedAttention(128, 2)
+    m.load_state_dict(g["weights"])
+    m.cuda()
+    q, k, v = (g[n].cuda().requires_grad_(True) for n in ("q", "k", "v"))
+    out, probs = m(q, k, v, return_attn=True)
+    assert out.shape == (2, 10, 128) and probs.shape == (2, 2, 10, 12)
+    assert rel(out, g["out"]) <= ACT_TOL and rel(probs, g["probs"]) <= ACT_TOL
+    (out * g["dy"].cuda()).sum().backward()
+    assert rel(q.grad, g["dq"]) <= GRAD_TOL and rel(k.grad, g["dk"]) <= GRAD_TOL and rel(v.grad, g["dv"]) <= GRAD_TOL
+    check_grads(m, g["grads"])
+
+
+def test_feed_forward():
+    from vit_core import FeedForwardBlock
+    g = load("ffn")
+    m = FeedForwardBlock(64, 128, dropout=0.0)
+    m.load_state_dict(g["weights"])
+    m.cuda()
+    x = g["x"].cuda().requires_grad_(True)
+    y = m(x)
+    assert rel(y, g["y"]) <= ACT_TOL
+    (y * g["dy"].cuda()).sum().backward()
+    assert rel(x.grad, g["dx"]) <= GRAD_TOL
+    check_grads(m, g["grads"])
+
+
+def test_patch_embeddings():
+    from vit_core import ConvolutionalPatchEmbedding, DynamicPatchEmbedding, ManualPatchEmbedding
+    g = load("patch_embeddings")
+    x = g["x"].cuda()
+    for name, cls in (("conv", ConvolutionalPatchEmbedding), ("manual", ManualPatchEmbedding)):
+        m = cls((3, 32, 32), 64, 8)
+        m.load_state_dict(g[name]["weights"])
+        y = m.cuda()(x)
+        assert y.shape == (3, 17, 64) and y.dtype == torch.float32
+        assert rel(y, g[name]["y"]) <= ACT_TOL, name
+    m = DynamicPatchEmbedding((3, 32, 32), 64, 8)
+    m.load_state_dict(g["dynamic"]["weights"])
+    m.cuda()
+    assert rel(m(x), g["dynamic"]["y"]) <= ACT_TOL
+    assert rel(m(g["dynamic"]["x_local"].cuda()), g["dynamic"]["y_local"]) <= ACT_TOL  # bicubic pos interpolation
+    with pytest.raises(ValueError):
+        m(torch.rand(1, 3, 30, 32, device="cuda"))
+
+
+def test_vit_supervised_step():
+    from vit_core import ViT
+    g = load("vit")
+    m = ViT(**g["cfg"])
+    m.load_state_dict(g["weights"])
+    m.cuda()
+    logits, probs = m(g["x"].cuda(), return_attn=True)
+    assert logits.shape == (4, 10) and logits.dtype == torch.float32
+    assert rel(logits, g["logits"]) <= ACT_TOL and rel(probs, g["probs"]) <= ACT_TOL
+    loss = F.cross_entropy(logits, g["labels"].cuda())
+    assert abs(loss.item() - g["loss"].item()) <= LOSS_TOL * abs(g["loss"].item())
+    loss.backward()
+    check_grads(m, g["grads"])
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert m(g["x"].cuda()).dtype == torch.bfloat16  # nn.Linear output dtype under autocast
+
+
+def _simmim(g):
+    from vit_core.ssl.simmim import SimMIMViT
+    import vit_core.ssl.simmim.model as mod
+    m = SimMIMViT(**g["cfg"])
+    m.load_state_dict(g["weights"])
+    m.cuda()
+    idx = g["perms"][:, : int(16 * 0.6)].cuda()
+    return m, mod, idx
+
+
+def test_simmim_forward_backward(monkeypatch):
+    g = load("simmim")
+    m, mod, idx = _simmim(g)
+    monkeypatch.setattr(mod, "draw_mask_indices", lambda B, N, r, dev: idx)
+    pred, targets, bool_mask = m(g["x"].cuda(), return_bool_mask=True)
+    assert torch.equal(bool_mask.squeeze(-1).cpu(), g["bool_mask"])          # mask bit-exact
+    assert torch.equal(targets.cpu().double(), g["targets"])                 # raw pixels bit-exact
+    assert rel(pred, g["pred"]) <= ACT_TOL
+    loss = torch.nn.L1Loss()(pred, targets)                                  # the reference trainer's criterion
+    assert abs(loss.item() - g["loss"].item()) <= LOSS_TOL * g["loss"].item()
+    loss.backward()
+    check_grads(m, g["grads"])
+    # fused objective path: same loss, same gradients
+    m.zero_grad()
+    loss2 = m.reconstruction_loss(g["x"].cuda())
+    assert abs(loss2.item() - g["loss"].item()) <= LOSS_TOL * g["loss"].item()
+    loss2.backward()
+    check_grads(m, g["grads"])
+    feats = m.inference_forward(g["x"].cuda())
+    assert not m.training and rel(feats, g["inference"]) <= ACT_TOL
+
+
+def test_simmim_mask_is_the_reference_rng_sequence():
+    """masking.py:22-25 draws B sequential torch.randperm(N, device)[:n_m]; replaying the device
+    generator must reproduce our mask bit for bit, and the derived tables must match the oracle."""
+    from vit_core.ssl.simmim.masking import draw_mask_indices, mask_tables, simple_masking
+    torch.manual_seed(1234)
+    B, N, r = 7, 196, 0.6
+    state = torch.cuda.get_rng_state()
+    ours = draw_mask_indices(B, N, r, torch.device("cuda"))
+    torch.cuda.set_rng_state(state)
+    ref = torch.stack([torch.randperm(N, device="cuda")[: int(N * r)] for _ in range(B)])
+    assert torch.equal(ours, ref)
+    bool_mask, rows, inv = mask_tables(ours, N)
+    perms = torch.cat([ours.cpu(), torch.zeros(B, N - ours.shape[1], dtype=torch.long)], dim=1)
+    assert torch.equal(bool_mask.cpu(), vit_ref.mask_from_perms(perms, N, r))
+    assert torch.equal(rows.cpu().long(), bool_mask.reshape(-1).nonzero().squeeze(1).cpu())
+    assert torch.equal((inv >= 0).cpu(), bool_mask.reshape(-1).cpu())
+    torch.cuda.set_rng_state(state)
+    patches = torch.rand(B, N, 48, device="cuda")
+    _, bm, tg = simple_masking(patches, r)
+    assert torch.equal(bm, bool_mask) and torch.equal(tg, patches[bm])
+
+
+def test_dino_forward_loss_backward_ema():
+    from vit_core.ssl.dino import DINOViT
+    from vit_core.ssl.dino.loss import DINOLoss
+    g = load("dino")
+    cfg, m, views, B = build_dino_case(DINOViT)
+    m.cuda()
+    m.train()
+    teacher, student = m([v.cuda() for v in views], 2)
+    assert teacher.shape == (2 * B, 512) and student.shape == (4 * B, 512)
+    assert not teacher.requires_grad and student.requires_grad
+    assert rel(teacher, g["teacher"]) <= ACT_TOL and rel(student, g["student"]) <= ACT_TOL
+    assert m.center.shape == (1, 512) and rel(m.center, g["center_after"]) <= ACT_TOL
+    crit = DINOLoss(*g["temps"])
+    loss = crit(teacher.view(2, B, 512), student.view(4, B, 512), m.center)
+    assert abs(loss.item() - g["loss"].item()) <= LOSS_TOL * abs(g["loss"].item())
+    loss.backward()
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        if k in g["grad_digests"]:
+            dg = g["grad_digests"][k]
+            mine = digest(p.grad)
+            e = ((mine["sample"] - dg["sample"]).abs().max() / dg["sample"].abs().max().clamp_min(1e-30)).item()
+            en = abs(mine["norm"] - dg["norm"]) / max(dg["norm"], 1e-30)
+            if max(e, en) > worst[1]:
+                worst = (k, max(e, en))
+        else:
+            assert p.grad is None, k  # teacher is frozen
+    assert worst[1] <= 2 * GRAD_TOL, worst
+    m.momentum_update_teacher(g["momentum"])
+    sd = m.state_dict()
+    for k, dg in g["teacher_after_digests"].items():
+        e = (digest(sd[k])["sample"] - dg["sample"]).abs().max().item()
+        assert e <= 1e-6 * max(1.0, dg["sample"].abs().max().item()), k
+    feats = m.inference_forward(views[0].cuda())
+    assert not m.training and feats.shape == (B, 512)
+
+
+def test_dino_loss_kernel_matches_reference_and_closed_form():
+    from vit_core.ssl.dino.loss import DINOLoss
+    g = load("dino_loss")
+    s = g["student"].cuda().requires_grad_(True)
+    loss = DINOLoss(*g["temps"])(g["teacher"].cuda(), s, g["center"].cuda())
+    # bf16 logits: compare against the oracle evaluated on the bf16-rounded inputs as well
+    tb, sb = g["teacher"].bfloat16().double(), g["student"].bfloat16().double()
+    ref_b = vit_ref.dino_loss(tb, sb, g["center"].double(), *g["temps"])
+    assert abs(loss.item() - ref_b.item()) <= LOSS_TOL * abs(ref_b.item())
+    assert abs(loss.item() - g["loss"].item()) <= 5e-3 * abs(g["loss"].item())
+    (loss * 65536.0).backward()  # GradScaler-style scaled backward
+    assert rel(s.grad / 65536.0, g["dstudent"]) <= 3e-2
+
+
+def test_no_cpu_fallback():
+    from vit_core import ViT
+    from vit_core._backend.lib import VitsslError
+    g = load("vit")
+    m = ViT(**g["cfg"])
+    with pytest.raises(VitsslError):
+        m(g["x"])  # CPU tensors: must fail loudly, never fall back

@@ -1,0 +1,633 @@
+"""Autograd glue: torch.autograd.Function wrappers that sequence the sm_100a kernels.
+
+Numerical contract (matches the reference under `autocast(bf16)`): parameters,
+the residual stream, LayerNorm statistics, losses and all gradients of parameters are fp32;
+GEMM / attention operands and their outputs are bf16 with fp32 accumulation.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .ops import EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_NONE
+
+
+# ----------------------------------------------------------------------------------------
+# bf16 weight shadows
+# ----------------------------------------------------------------------------------------
+def _cache_of(owner) -> dict:
+    c = owner.__dict__.get("_vitssl_cache")
+    if c is None:
+        c = {}
+        object.__setattr__(owner, "_vitssl_cache", c)
+    return c
+
+
+def bf16_shadows(requests):
+    """requests: list of (owner_module, key, [fp32 params]) -> list of bf16 tensors.
+
+    Each shadow is the row-wise concatenation of its params (viewed 2-D). Stale shadows (parameter
+    version or storage changed) are refreshed with ONE multi-tensor cast launch for the whole list.
+    """
+    outs, srcs, dsts = [], [], []
+    for owner, key, params in requests:
+        cache = _cache_of(owner)
+        sig = tuple((p.data_ptr(), p._version) for p in params)
+        ent = cache.get(key)
+        dev = params[0].device
+        if ent is not None and ent[1] == sig and ent[0].device == dev:
+            outs.append(ent[0])
+            continue
+        rows = sum(p.shape[0] for p in params)
+        cols = params[0].numel() // params[0].shape[0]
+        if ent is not None and ent[0].shape == (rows, cols) and ent[0].device == dev:
+            buf = ent[0]
+        else:
+            buf = torch.empty((rows, cols), device=dev, dtype=torch.bfloat16)
+        r = 0
+        for p in params:
+            pd = p.detach()
+            srcs.append(pd if pd.is_contiguous() else pd.contiguous())
+            dsts.append(buf[r:r + p.shape[0]])
+            r += p.shape[0]
+        cache[key] = (buf, sig)
+        outs.append(buf)
+    if srcs:
+        ops.multi_cast_bf16(srcs, dsts)
+    return outs
+
+
+def _new_seed() -> int:
+    # CPU generator: deterministic under torch.manual_seed, no device sync
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def _as_bf16(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype == torch.bfloat16:
+        return x if x.is_contiguous() else x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    return ops.cast_bf16(x if x.is_contiguous() else x.contiguous())
+
+
+def autocast_out(y: torch.Tensor) -> torch.Tensor:
+    """Linear outputs are bf16 inside autocast (like the reference) and fp32 outside it."""
+    if torch.is_autocast_enabled():
+        return y
+    return y.float() if y.dtype != torch.float32 else y
+
+
+# ----------------------------------------------------------------------------------------
+# attention core shared by the encoder stack and MultiHeadedAttention
+# ----------------------------------------------------------------------------------------
+def _attn_fwd(q, k, v, H, want_lse):
+    """q: [B,Sq,D] bf16 view, k/v: [B,Sk,D] views (unit inner stride). Returns (ctx [B,Sq,D], lse)."""
+    B, Sq, D = q.shape
+    Sk = k.shape[1]
+    dk = D // H
+    scale = 1.0 / math.sqrt(dk)
+    if ops.attention_supported(Sq, Sk, dk):
+        return ops.attention_fwd(q, k, v, H, scale, want_lse=want_lse)
+    qh, kh, vh = (t.unflatten(2, (H, dk)).transpose(1, 2) for t in (q, k, v))
+    out, _, lse = ops.attention_generic_fwd(qh, kh, vh, scale, want_probs=False, want_lse=want_lse)
+    return out.transpose(1, 2).reshape(B, Sq, D), lse
+
+
+def _attn_bwd(q, k, v, ctx_, dctx, lse, H, dq, dk_, dv):
+    B, Sq, D = q.shape
+    Sk = k.shape[1]
+    dk = D // H
+    scale = 1.0 / math.sqrt(dk)
+    if ops.attention_supported(Sq, Sk, dk) and Sq <= 256:
+        ops.attention_bwd(q, k, v, ctx_, dctx, lse, H, scale, dq, dk_, dv)
+        return
+    qh, kh, vh = (t.unflatten(2, (H, dk)).transpose(1, 2) for t in (q, k, v))
+    oh = ctx_.unflatten(2, (H, dk)).transpose(1, 2)
+    doh = dctx.unflatten(2, (H, dk)).transpose(1, 2)
+    gq, gk, gv = ops.attention_generic_bwd(qh, kh, vh, oh, doh, lse, scale)
+    dq.copy_(gq.transpose(1, 2).reshape(B, Sq, D))
+    dk_.copy_(gk.reshape(B, Sk, D))
+    dv.copy_(gv.reshape(B, Sk, D))
+
+
+def attention_probs(q, k, H):
+    """fp32 probabilities [B,H,Sq,Sk] (return_attn=True path, attention.py:24-25)."""
+    B, Sq, D = q.shape
+    dk = D // H
+    qh, kh = (t.unflatten(2, (H, dk)).transpose(1, 2) for t in (q, k))
+    _, probs, _ = ops.attention_generic_fwd(qh, kh, kh, 1.0 / math.sqrt(dk), want_probs=True, want_lse=False)
+    return probs
+
+
+# ----------------------------------------------------------------------------------------
+# encoder stack: L pre-LN blocks in one autograd node (encoder_block.py:32-53)
+# params per block (12): wq wk wv wo | w1 b1 w2 b2 | g1 be1 g2 be2
+# dropout sites per block l: 3l (after out-proj), 3l+1 (after GELU), 3l+2 (after FFN)
+# ----------------------------------------------------------------------------------------
+class _EncoderStackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, *params):
+        L, H = meta.L, meta.H
+        B, S, D = x.shape
+        M = B * S
+        need_grad = any(ctx.needs_input_grad)
+        p = meta.p if meta.training else 0.0
+        seed = _new_seed() if p > 0 else 0
+        x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+        stream = x.view(M, D)
+        branch = None
+        saved = []
+        last_qkv = None
+        for l in range(L):
+            wqkv, wo, w1, w2 = meta.weights[l]
+            _, _, _, _, _, b1, _, b2, g1, be1, g2, be2 = params[12 * l:12 * l + 12]
+            F_ = w1.shape[0]
+            xs, xn1, mean1, rstd1 = ops.add_layernorm_fwd(
+                stream, branch, g1, be1, dropout_p=p if branch is not None else 0.0, seed=seed,
+                offset=max(3 * l - 1, 0))
+            qkv = ops.gemm(xn1, wqkv)
+            qkv3 = qkv.view(B, S, 3 * D)
+            ctx_, lse = _attn_fwd(qkv3[..., :D], qkv3[..., D:2 * D], qkv3[..., 2 * D:], H, need_grad)
+            y1 = ops.gemm(ctx_.view(M, D), wo)
+            xmid, xn2, mean2, rstd2 = ops.add_layernorm_fwd(xs, y1, g2, be2, dropout_p=p, seed=seed,
+                                                            offset=3 * l)
+            u = torch.empty((M, F_), device=x.device, dtype=torch.bfloat16)
+            h = ops.gemm(xn2, w1, epilogue=EPI_BIAS_GELU, bias=b1, aux=u, dropout_p=p, seed=seed,
+                         offset=3 * l + 1)
+            y2 = ops.gemm(h, w2, epilogue=EPI_BIAS, bias=b2)
+            stream, branch = xmid, y2
+            last_qkv = qkv3
+            if need_grad:
+                saved.append((xs, mean1, rstd1, xn1, qkv3, ctx_, lse, xmid, mean2, rstd2, xn2, u, h))
+        out, _, _, _ = ops.add_layernorm_fwd(stream, branch, None, None, dropout_p=p, seed=seed,
+                                             offset=3 * L - 1)
+        probs = None
+        if meta.return_attn:
+            probs = attention_probs(last_qkv[..., :D], last_qkv[..., D:2 * D], H)
+        if need_grad:
+            ctx.saved = saved
+            ctx.meta = meta
+            ctx.params = params
+            ctx.p, ctx.seed = p, seed
+            ctx.shape = (B, S, D)
+        out = out.view(B, S, D)
+        if probs is not None:
+            ctx.mark_non_differentiable(probs)
+            return out, probs
+        return out
+
+    @staticmethod
+    def backward(ctx, gout, *_):
+        meta, params, saved = ctx.meta, ctx.params, ctx.saved
+        L, H = meta.L, meta.H
+        B, S, D = ctx.shape
+        M = B * S
+        p, seed = ctx.p, ctx.seed
+        g = gout if (gout.dtype == torch.float32 and gout.is_contiguous()) else gout.float().contiguous()
+        gs = g.view(M, D)
+        _, dbranch, _, _ = ops.add_layernorm_bwd(None, None, None, None, None, gs, want_dx=False,
+                                                 want_dbranch=True, dropout_p=p, seed=seed,
+                                                 offset=3 * L - 1)
+        grads: List[Optional[torch.Tensor]] = [None] * (12 * L)
+        for l in reversed(range(L)):
+            wqkv, wo, w1, w2 = meta.weights[l]
+            g1, g2 = params[12 * l + 8], params[12 * l + 10]
+            xs, mean1, rstd1, xn1, qkv3, ctx_, lse, xmid, mean2, rstd2, xn2, u, h = saved[l]
+            saved[l] = None
+            dy2 = dbranch
+            du = ops.gemm(dy2, w2, b_mn=True, epilogue=EPI_DGELU, aux=u, dropout_p=p, seed=seed,
+                          offset=3 * l + 1)
+            dW2 = ops.gemm(dy2, h, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
+            db2 = ops.colsum_bf16(dy2)
+            dxn2 = ops.gemm(du, w1, b_mn=True)
+            dW1 = ops.gemm(du, xn2, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
+            db1 = ops.colsum_bf16(du)
+            del du, u, h
+            gs, dy1, dg2, dbe2 = ops.add_layernorm_bwd(dxn2, xmid, mean2, rstd2, g2, gs,
+                                                       want_dbranch=True, dropout_p=p, seed=seed,
+                                                       offset=3 * l)
+            dctx = ops.gemm(dy1, wo, b_mn=True)
+            dWo = ops.gemm(dy1, ctx_.view(M, D), a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
+            dqkv = torch.empty((B, S, 3 * D), device=g.device, dtype=torch.bfloat16)
+            _attn_bwd(qkv3[..., :D], qkv3[..., D:2 * D], qkv3[..., 2 * D:], ctx_, dctx.view(B, S, D), lse, H,
+                      dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:])
+            dqkv2 = dqkv.view(M, 3 * D)
+            dxn1 = ops.gemm(dqkv2, wqkv, b_mn=True)
+            dWqkv = ops.gemm(dqkv2, xn1, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
+            gs, dbranch, dg1, dbe1 = ops.add_layernorm_bwd(dxn1, xs, mean1, rstd1, g1, gs,
+                                                           want_dbranch=(l > 0), dropout_p=p if l > 0 else 0.0,
+                                                           seed=seed, offset=max(3 * l - 1, 0))
+            grads[12 * l:12 * l + 12] = [dWqkv[:D], dWqkv[D:2 * D], dWqkv[2 * D:], dWo, dW1, db1, dW2, db2,
+                                         dg1, dbe1, dg2, dbe2]
+        for i, need in enumerate(ctx.needs_input_grad[2:]):
+            if not need:
+                grads[i] = None
+        dx = gs.view(B, S, D) if ctx.needs_input_grad[0] else None
+        return (dx, None, *grads)
+
+
+def block_params(blk) -> list:
+    a, f = blk.self_attention, blk.feed_forward
+    return [a.w_query.weight, a.w_key.weight, a.w_value.weight, a.final_linear.weight,
+            f.linear_in.weight, f.linear_in.bias, f.linear_out.weight, f.linear_out.bias,
+            blk.layer_norm1.weight, blk.layer_norm1.bias, blk.layer_norm2.weight, blk.layer_norm2.bias]
+
+
+def encoder_stack(blocks: Sequence, x: torch.Tensor, return_attn: bool = False):
+    """Run a sequence of EncoderBlock modules as one fused autograd node.
+
+    Returns (x_out fp32 [B,S,D], probs of the LAST block or None) — vit.py:35-45.
+    """
+    blocks = list(blocks)
+    if not blocks:
+        return x, None
+    reqs = []
+    for blk in blocks:
+        a, f = blk.self_attention, blk.feed_forward
+        reqs += [(a, "wqkv", [a.w_query.weight, a.w_key.weight, a.w_value.weight]),
+                 (a, "wo", [a.final_linear.weight]),
+                 (f, "w1", [f.linear_in.weight]),
+                 (f, "w2", [f.linear_out.weight])]
+    sh = bf16_shadows(reqs)
+    b0 = blocks[0]
+    meta = SimpleNamespace(
+        L=len(blocks), H=b0.self_attention.num_heads, p=float(b0.drop1.p),
+        training=bool(b0.training), return_attn=bool(return_attn),
+        weights=[tuple(sh[4 * i:4 * i + 4]) for i in range(len(blocks))])
+    params = []
+    for blk in blocks:
+        params += block_params(blk)
+    out = _EncoderStackFn.apply(x, meta, *params)
+    if return_attn:
+        return out[0], out[1]
+    return out, None
+
+
+# ----------------------------------------------------------------------------------------
+# generic MLP: chain of Linear(+GELU)(+dropout after GELU). Used by FeedForwardBlock
+# (feed_forward.py:26-28), the DINO head MLP (ssl/dino/head.py:10-16) and plain linears.
+# ----------------------------------------------------------------------------------------
+class _MLPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, *params):
+        # params: (w, b) per layer (b may be None); meta.weights: bf16 shadows; meta.gelu: flags
+        n = len(meta.gelu)
+        lead = x.shape[:-1]
+        xb = _as_bf16(x.reshape(-1, x.shape[-1]))
+        need_grad = any(ctx.needs_input_grad)
+        p = meta.p if meta.training else 0.0
+        seed = _new_seed() if p > 0 else 0
+        acts, pre = [xb], []
+        cur = xb
+        for i in range(n):
+            w, b = meta.weights[i], params[2 * i + 1]
+            last = i == n - 1
+            out_dtype = meta.out_dtype if last else torch.bfloat16
+            if meta.gelu[i]:
+                u = torch.empty((cur.shape[0], w.shape[0]), device=cur.device, dtype=torch.bfloat16)
+                cur = ops.gemm(cur, w, epilogue=EPI_BIAS_GELU, bias=b, aux=u, dropout_p=p, seed=seed, offset=i)
+                pre.append(u)
+            else:
+                cur = ops.gemm(cur, w, epilogue=EPI_BIAS if b is not None else EPI_NONE, bias=b,
+                               out_dtype=out_dtype)
+                pre.append(None)
+            if not last:
+                acts.append(cur)
+        if need_grad:
+            ctx.acts, ctx.pre, ctx.meta, ctx.p, ctx.seed = acts, pre, meta, p, seed
+            ctx.in_dtype, ctx.in_shape = x.dtype, x.shape
+        return cur.view(*lead, cur.shape[-1])
+
+    @staticmethod
+    def backward(ctx, gout):
+        meta, acts, pre = ctx.meta, ctx.acts, ctx.pre
+        n = len(meta.gelu)
+        p, seed = ctx.p, ctx.seed
+        dy = _as_bf16(gout.reshape(-1, gout.shape[-1]))
+        grads = [None] * (2 * n)
+        for i in reversed(range(n)):
+            w = meta.weights[i]
+            # dy is the gradient of layer i's linear output (pre-activation) here
+            if ctx.needs_input_grad[2 + 2 * i]:
+                grads[2 * i] = ops.gemm(dy, acts[i], a_mn=True, b_mn=True, out_dtype=torch.float32,
+                                        split_k=-1).view(meta.wshapes[i])
+            if ctx.needs_input_grad[3 + 2 * i]:
+                grads[2 * i + 1] = ops.colsum_bf16(dy)
+            if i > 0:
+                if meta.gelu[i - 1]:
+                    dy = ops.gemm(dy, w, b_mn=True, epilogue=EPI_DGELU, aux=pre[i - 1], dropout_p=p,
+                                  seed=seed, offset=i - 1)
+                else:
+                    dy = ops.gemm(dy, w, b_mn=True)
+            elif ctx.needs_input_grad[0]:
+                dy = ops.gemm(dy, w, b_mn=True, out_dtype=torch.float32 if ctx.in_dtype == torch.float32
+                              else torch.bfloat16)
+        dx = dy.view(ctx.in_shape).to(ctx.in_dtype) if ctx.needs_input_grad[0] else None
+        return (dx, None, *grads)
+
+
+def mlp(x, owner_layers, gelu_flags, *, dropout_p=0.0, training=False, out_dtype=torch.bfloat16):
+    """owner_layers: list of modules with .weight [N,K...] and optional .bias."""
+    reqs = [(m, "w", [m.weight]) for m in owner_layers]
+    sh = bf16_shadows(reqs)
+    meta = SimpleNamespace(gelu=list(gelu_flags), weights=sh, p=float(dropout_p), training=bool(training),
+                           out_dtype=out_dtype, wshapes=[m.weight.shape for m in owner_layers])
+    params = []
+    for m in owner_layers:
+        params += [m.weight, getattr(m, "bias", None)]
+    return _MLPFn.apply(x, meta, *params)
+
+
+# ----------------------------------------------------------------------------------------
+# MultiHeadedAttention with arbitrary query / key / value inputs (attention.py:61-106)
+# ----------------------------------------------------------------------------------------
+class _MHAFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_in, k_in, v_in, meta, wq, wk, wv, wo):
+        H = meta.H
+        B, Sq, D = q_in.shape
+        Sk = k_in.shape[1]
+        same = meta.same
+        wqkv, wob = meta.weights
+        qb = _as_bf16(q_in.reshape(-1, D))
+        if same:
+            qkv = ops.gemm(qb, wqkv).view(B, Sq, 3 * D)
+            q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+            kb = vb = qb
+        else:
+            kb = _as_bf16(k_in.reshape(-1, D))
+            vb = _as_bf16(v_in.reshape(-1, D))
+            q = ops.gemm(qb, wqkv[:D]).view(B, Sq, D)
+            k = ops.gemm(kb, wqkv[D:2 * D]).view(B, Sk, D)
+            v = ops.gemm(vb, wqkv[2 * D:]).view(B, Sk, D)
+        ctx_, lse = _attn_fwd(q, k, v, H, True)
+        out = ops.gemm(ctx_.view(-1, D), wob).view(B, Sq, D)
+        probs = attention_probs(q, k, H) if meta.return_attn else None
+        ctx.saved = (qb, kb, vb, q, k, v, ctx_, lse)
+        ctx.meta = meta
+        ctx.in_dtype = q_in.dtype
+        if probs is not None:
+            ctx.mark_non_differentiable(probs)
+            return out, probs
+        return out
+
+    @staticmethod
+    def backward(ctx, gout, *_):
+        meta = ctx.meta
+        H = meta.H
+        qb, kb, vb, q, k, v, ctx_, lse = ctx.saved
+        wqkv, wob = meta.weights
+        B, Sq, D = q.shape
+        Sk = k.shape[1]
+        dy = _as_bf16(gout.reshape(-1, D))
+        dctx = ops.gemm(dy, wob, b_mn=True).view(B, Sq, D)
+        dWo = ops.gemm(dy, ctx_.view(-1, D), a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
+        f32 = torch.float32
+        if meta.same:
+            dqkv = torch.empty((B, Sq, 3 * D), device=dy.device, dtype=torch.bfloat16)
+            _attn_bwd(q, k, v, ctx_, dctx, lse, H, dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:])
+            d2 = dqkv.view(-1, 3 * D)
+            dx = ops.gemm(d2, wqkv, b_mn=True, out_dtype=f32).view(B, Sq, D)
+            dW = ops.gemm(d2, qb, a_mn=True, b_mn=True, out_dtype=f32, split_k=-1)
+            third = dx / 3.0  # the same tensor was passed three times: autograd sums the three slots
+            return third, third, third, None, dW[:D], dW[D:2 * D], dW[2 * D:], dWo
+        dq = torch.empty((B, Sq, D), device=dy.device, dtype=torch.bfloat16)
+        dk = torch.empty((B, Sk, D), device=dy.device, dtype=torch.bfloat16)
+        dv = torch.empty((B, Sk, D), device=dy.device, dtype=torch.bfloat16)
+        _attn_bwd(q, k, v, ctx_, dctx, lse, H, dq, dk, dv)
+        outs = []
+        for g_, w_, xb_, S_ in ((dq, wqkv[:D], qb, Sq), (dk, wqkv[D:2 * D], kb, Sk), (dv, wqkv[2 * D:], vb, Sk)):
+            g2 = g_.view(-1, D)
+            outs.append((ops.gemm(g2, w_, b_mn=True, out_dtype=f32).view(B, S_, D),
+                         ops.gemm(g2, xb_, a_mn=True, b_mn=True, out_dtype=f32, split_k=-1)))
+        return (outs[0][0], outs[1][0], outs[2][0], None, outs[0][1], outs[1][1], outs[2][1], dWo)
+
+
+def multi_head_attention(mod, query, key, value, return_attn=False):
+    wqkv, wo = bf16_shadows([(mod, "wqkv", [mod.w_query.weight, mod.w_key.weight, mod.w_value.weight]),
+                             (mod, "wo", [mod.final_linear.weight])])
+    same = (query is key) and (key is value)
+    meta = SimpleNamespace(H=mod.num_heads, same=same, weights=(wqkv, wo), return_attn=bool(return_attn))
+    out = _MHAFn.apply(query, key, value, meta, mod.w_query.weight, mod.w_key.weight, mod.w_value.weight,
+                       mod.final_linear.weight)
+    if return_attn:
+        return out[0], out[1]
+    return out, None
+
+
+# ----------------------------------------------------------------------------------------
+# ScaledDotProductAttention on already-projected heads (attention.py:5-27), any head dim
+# ----------------------------------------------------------------------------------------
+class _SDPAFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, return_attn):
+        lead = q.shape[:-2]
+        Sq, d = q.shape[-2:]
+        Sk = k.shape[-2]
+        qb = _as_bf16(q.reshape(-1, 1, Sq, d))
+        kb = _as_bf16(k.reshape(-1, 1, Sk, d))
+        vb = _as_bf16(v.reshape(-1, 1, Sk, d))
+        scale = 1.0 / math.sqrt(d)
+        out, probs, lse = ops.attention_generic_fwd(qb, kb, vb, scale, want_probs=return_attn, want_lse=True)
+        ctx.saved = (qb, kb, vb, out, lse)
+        ctx.scale, ctx.dt, ctx.shapes = scale, q.dtype, (q.shape, k.shape, v.shape)
+        o = out.view(*lead, Sq, d).to(q.dtype)
+        if return_attn:
+            probs = probs.view(*lead, Sq, Sk)
+            ctx.mark_non_differentiable(probs)
+            return o, probs
+        return o
+
+    @staticmethod
+    def backward(ctx, gout, *_):
+        qb, kb, vb, out, lse = ctx.saved
+        go = _as_bf16(gout.reshape(out.shape))
+        dq, dk, dv = ops.attention_generic_bwd(qb, kb, vb, out, go, lse, ctx.scale)
+        qs, ks, vs = ctx.shapes
+        return (dq.view(qs).to(ctx.dt), dk.transpose(1, 2).reshape(ks).to(ctx.dt),
+                dv.transpose(1, 2).reshape(vs).to(ctx.dt), None)
+
+
+def scaled_dot_product_attention(q, k, v, return_attn=False):
+    out = _SDPAFn.apply(q, k, v, bool(return_attn))
+    if return_attn:
+        return out[0], out[1]
+    return out, None
+
+
+# ----------------------------------------------------------------------------------------
+# stand-alone LayerNorm (MLPHead.norm, mlp_head.py:9,13): fp32 rows in, bf16 out
+# ----------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        D = x.shape[-1]
+        x2 = x if (x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32) else x.float().reshape(-1, D).contiguous()
+        _, y, mean, rstd = ops.add_layernorm_fwd(x2, None, gamma, beta, eps=eps)
+        ctx.saved = (x2, mean, rstd, gamma)
+        ctx.in_shape, ctx.in_dtype = x.shape, x.dtype
+        return y.view(*x.shape[:-1], D)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x2, mean, rstd, gamma = ctx.saved
+        dy = _as_bf16(gout.reshape(-1, gout.shape[-1]))
+        dx, _, dg, db = ops.add_layernorm_bwd(dy, x2, mean, rstd, gamma, None)
+        return dx.view(ctx.in_shape).to(ctx.in_dtype), dg, db, None
+
+
+def layer_norm(x, ln_module):
+    return _LayerNormFn.apply(x, ln_module.weight, ln_module.bias, float(ln_module.eps))
+
+
+# ----------------------------------------------------------------------------------------
+# patch embedding: im2col + projection GEMM + token assembly
+# (patch_embedding.py:50-63, 90-96, 122-128; ssl/simmim/model.py:43-49)
+# ----------------------------------------------------------------------------------------
+class _EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, meta, weight, bias, cls, pos, mask_token):
+        p = meta.patch
+        img = img if (img.dtype == torch.float32 and img.is_contiguous()) else img.float().contiguous()
+        B, C, Hh, Ww = img.shape
+        N = (Hh // p) * (Ww // p)
+        D = weight.shape[0]
+        patches = ops.im2col_bf16(img, p)
+        proj = ops.gemm(patches, meta.w_bf16, epilogue=EPI_BIAS, bias=bias)
+        cls_v = cls.reshape(-1).contiguous() if cls is not None else None
+        pos_v = pos.reshape(-1, D).contiguous()
+        mt_v = mask_token.reshape(-1).contiguous() if mask_token is not None else None
+        x = ops.embed_tokens_fwd(proj, cls_v, pos_v, meta.mask_u8 if mask_token is not None else None, mt_v, B, N, D)
+        ctx.saved = (patches,)
+        ctx.meta, ctx.dims = meta, (B, N, D)
+        ctx.shapes = (weight.shape, None if cls is None else cls.shape, pos.shape,
+                      None if mask_token is None else mask_token.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        (patches,) = ctx.saved
+        meta = ctx.meta
+        B, N, D = ctx.dims
+        wshape, cshape, pshape, mshape = ctx.shapes
+        g = gx if gx.dtype == torch.float32 else gx.float()
+        if g.stride(2) != 1:
+            g = g.contiguous()
+        has_cls = cshape is not None
+        dproj, dpos, dmt = ops.embed_tokens_bwd(g, meta.mask_u8 if mshape is not None else None, B, N, D,
+                                                has_cls, mshape is not None)
+        dW = ops.gemm(dproj, patches, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1).view(wshape)
+        db = ops.colsum_bf16(dproj)
+        dcls = dpos[0].reshape(cshape).clone() if has_cls else None
+        return (None, None, dW, db, dcls, dpos.view(pshape), None if dmt is None else dmt.view(mshape))
+
+
+def embed_patches(img, owner, weight, bias, cls, pos, patch, mask_u8=None, mask_token=None):
+    (w_bf16,) = bf16_shadows([(owner, "wproj", [weight])])
+    meta = SimpleNamespace(patch=int(patch), w_bf16=w_bf16, mask_u8=mask_u8)
+    return _EmbedFn.apply(img, meta, weight, bias, cls, pos, mask_token)
+
+
+# ----------------------------------------------------------------------------------------
+# SimMIM: masked-row gather and fused L1 loss
+# ----------------------------------------------------------------------------------------
+class _GatherRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, inv_idx):
+        B, S, D = x.shape
+        x2 = x.reshape(B * S, D)
+        ctx.saved = (inv_idx,)
+        ctx.shape = (B, S, D)
+        return ops.gather_rows_bf16(x2, idx)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (inv_idx,) = ctx.saved
+        B, S, D = ctx.shape
+        return ops.scatter_rows_f32(_as_bf16(gy), inv_idx, B * S).view(B, S, D), None, None
+
+
+def gather_rows(x, idx, inv_idx):
+    return _GatherRowsFn.apply(x, idx, inv_idx)
+
+
+class _L1LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        pb = _as_bf16(pred)
+        tg = target if (target.dtype == torch.float32 and target.is_contiguous()) else target.float().contiguous()
+        loss, sign = ops.l1_loss_fwd(pb, tg, want_sign=ctx.needs_input_grad[0])
+        ctx.saved = (sign,)
+        ctx.n, ctx.dt = pb.numel(), pred.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        (sign,) = ctx.saved
+        return (sign * (go / ctx.n).to(sign.dtype)).to(ctx.dt), None
+
+
+def l1_loss(pred, target):
+    """mean |pred - target| with the sign tensor kept for backward (nn.L1Loss(mean) semantics)."""
+    return _L1LossFn.apply(pred, target)
+
+
+# ----------------------------------------------------------------------------------------
+# DINO head tail: F.normalize + weight-normed Linear (ssl/dino/head.py:17,21-22)
+# ----------------------------------------------------------------------------------------
+class _NormLinearWNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, g, v, bias, out_dtype):
+        zb = _as_bf16(z.reshape(-1, z.shape[-1]))
+        zn, inv_z = ops.l2norm_fwd(zb)
+        w, inv_v = ops.weight_norm_fwd(v.detach().contiguous(), g.detach().reshape(-1).contiguous())
+        logits = ops.gemm(zn, w, epilogue=EPI_BIAS, bias=bias, out_dtype=out_dtype)
+        need = any(ctx.needs_input_grad)
+        if need:
+            ctx.saved = (zb, zn, inv_z, w, inv_v, g, v)
+            ctx.in_dtype, ctx.in_shape = z.dtype, z.shape
+        return logits
+
+    @staticmethod
+    def backward(ctx, gl):
+        zb, zn, inv_z, w, inv_v, g, v = ctx.saved
+        dl = _as_bf16(gl)
+        dzn = ops.gemm(dl, w, b_mn=True)
+        dz = ops.l2norm_bwd(zb, inv_z, dzn)
+        dW = ops.gemm(dl, zn, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
+        dbias = ops.colsum_bf16(dl)
+        dg, dv = ops.weight_norm_bwd(dW, v.detach().contiguous(), g.detach().reshape(-1).contiguous(), inv_v)
+        return dz.view(ctx.in_shape).to(ctx.in_dtype), dg.view(g.shape), dv, dbias, None
+
+
+def normalize_wn_linear(z, g, v, bias, out_dtype=torch.bfloat16):
+    return _NormLinearWNFn.apply(z, g, v, bias, out_dtype)
+
+
+# ----------------------------------------------------------------------------------------
+# DINO loss (ssl/dino/loss.py:13-29) — factorised single-pass kernels
+# ----------------------------------------------------------------------------------------
+class _DinoLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, teacher, student, center, tt, ts):
+        tb, sb = _as_bf16(teacher), _as_bf16(student)
+        c = center.reshape(-1).float().contiguous()
+        loss, t_stats, s_lse = ops.dino_loss_fwd(tb, sb, c, tt, ts)
+        ctx.saved = (tb, sb, c, t_stats, s_lse)
+        ctx.temps, ctx.dt = (tt, ts), student.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        tb, sb, c, t_stats, s_lse = ctx.saved
+        tt, ts = ctx.temps
+        ds = ops.dino_loss_bwd(tb, sb, c, t_stats, s_lse, go, tt, ts)
+        return None, ds.to(ctx.dt), None, None, None
+
+
+def dino_loss(teacher, student, center, teacher_temp, student_temp):
+    return _DinoLossFn.apply(teacher.detach(), student, center.detach(), float(teacher_temp), float(student_temp))

@@ -28,6 +28,31 @@ SIGNATURES = {}
 # ld_aux | alpha | out_fp32, split_k | dropout_p | seed, offset | stream)
 SIGNATURES["vitssl_gemm_bf16"] = "ppp" + "llllll" + "iii" + "pp" + "l" + "f" + "ii" + "f" + "uu" + "s"
 
+SIGNATURES["vitssl_add_layernorm_fwd"] = "plpp" + "pp" + "ppp" + "ll" + "ff" + "uu" + "s"
+SIGNATURES["vitssl_add_layernorm_bwd"] = "ppl" + "ppp" + "pl" + "pl" + "p" + "pp" + "ll" + "f" + "uu" + "s"
+SIGNATURES["vitssl_attention_supported"] = "lll"
+SIGNATURES["vitssl_attention_fwd"] = "ppp" + "lll" + "pl" + "p" + "llll" + "f" + "s"
+SIGNATURES["vitssl_attention_bwd"] = "ppp" + "lll" + "ppl" + "p" + "pl" + "pl" + "pl" + "llll" + "f" + "s"
+SIGNATURES["vitssl_attention_generic_fwd"] = "ppp" + "p" + "ppp" + "lllll" + "f" + "s"
+SIGNATURES["vitssl_attention_generic_bwd"] = "ppp" + "p" + "pp" + "p" + "ppp" + "lllll" + "f" + "s"
+SIGNATURES["vitssl_multi_cast_bf16"] = "pppis"
+SIGNATURES["vitssl_multi_ema"] = "pppifs"
+SIGNATURES["vitssl_colsum_bf16"] = "plllps"
+SIGNATURES["vitssl_im2col_bf16"] = "pp" + "lllll" + "s"
+SIGNATURES["vitssl_gather_patches_f32"] = "ppp" + "lllll" + "s"
+SIGNATURES["vitssl_embed_tokens_fwd"] = "pppppp" + "lll" + "s"
+SIGNATURES["vitssl_embed_tokens_bwd"] = "pllp" + "ppp" + "lll" + "i" + "s"
+SIGNATURES["vitssl_gather_rows_bf16"] = "plppll" + "s"
+SIGNATURES["vitssl_scatter_rows_f32"] = "pppll" + "s"
+SIGNATURES["vitssl_l1_loss_fwd"] = "ppppl" + "s"
+SIGNATURES["vitssl_l2norm_fwd"] = "pppll" + "s"
+SIGNATURES["vitssl_l2norm_bwd"] = "ppppll" + "s"
+SIGNATURES["vitssl_weight_norm_fwd"] = "ppppll" + "s"
+SIGNATURES["vitssl_weight_norm_bwd"] = "pppppp" + "ll" + "s"
+SIGNATURES["vitssl_center_ema"] = "ppplff" + "s"
+SIGNATURES["vitssl_dino_loss_fwd"] = "pppppp" + "llll" + "ff" + "s"
+SIGNATURES["vitssl_dino_loss_bwd"] = "ppppppp" + "llll" + "ff" + "s"
+
 _lib = None
 
 

@@ -60,3 +60,326 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_NONE, bias=None, aux=None
         int(seed), int(offset), _l.stream_ptr(),
     )
     return out
+
+
+def add_layernorm_fwd(x, branch, gamma, beta, *, eps=1e-5, dropout_p=0.0, seed=0, offset=0):
+    """x: fp32 [..., D] rows (last dim contiguous, uniform row pitch); branch: bf16 dense or None.
+
+    Returns (x_out fp32 dense | x itself when branch is None, y bf16 | None, mean, rstd).
+    """
+    _l.ensure_device()
+    _check_cuda(x, branch, gamma, beta)
+    D = x.shape[-1]
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    x2 = x.reshape(-1, D) if x.is_contiguous() else x
+    assert x2.dim() == 2, "strided LayerNorm input must be 2-D"
+    rows, ldx = x2.shape[0], x2.stride(0)
+    x_out = None
+    if branch is not None:
+        assert branch.dtype == torch.bfloat16 and branch.is_contiguous() and branch.numel() == rows * D
+        x_out = torch.empty((rows, D), device=x.device, dtype=torch.float32)
+    y = mean = rstd = None
+    if gamma is not None:
+        y = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _l.call("vitssl_add_layernorm_fwd", _p(x2), ldx, _p(branch), _p(x_out), _p(gamma), _p(beta),
+            _p(y), _p(mean), _p(rstd), rows, D, float(eps), float(dropout_p), int(seed), int(offset),
+            _l.stream_ptr())
+    return (x_out if x_out is not None else x2), y, mean, rstd
+
+
+def add_layernorm_bwd(dy, x, mean, rstd, gamma, dres, *, want_dx=True, want_dbranch=False,
+                      dropout_p=0.0, seed=0, offset=0, dx_out=None):
+    """Returns (dx fp32 | None, dbranch bf16 | None, dgamma | None, dbeta | None)."""
+    _l.ensure_device()
+    ref = dy if dy is not None else dres
+    D = ref.shape[-1]
+    rows = ref.numel() // D if ref.is_contiguous() else ref.shape[0]
+    dev = ref.device
+    ldx = 0
+    if dy is not None:
+        assert dy.dtype == torch.bfloat16 and dy.is_contiguous()
+        assert x.dtype == torch.float32 and x.stride(-1) == 1
+        ldx = x.stride(-2) if x.dim() >= 2 else D
+    ld_dres = 0
+    if dres is not None:
+        assert dres.dtype == torch.float32 and dres.stride(-1) == 1
+        ld_dres = dres.stride(-2) if dres.dim() >= 2 else D
+    dx = None
+    ld_dx = 0
+    if dx_out is not None:
+        dx = dx_out
+        ld_dx = dx.stride(-2)
+    elif want_dx:
+        dx = torch.empty((rows, D), device=dev, dtype=torch.float32)
+        ld_dx = D
+    dbranch = torch.empty((rows, D), device=dev, dtype=torch.bfloat16) if want_dbranch else None
+    dgamma = dbeta = None
+    if dy is not None:
+        dgamma = torch.empty(D, device=dev, dtype=torch.float32)
+        dbeta = torch.empty(D, device=dev, dtype=torch.float32)
+    _l.call("vitssl_add_layernorm_bwd", _p(dy), _p(x), ldx, _p(mean), _p(rstd), _p(gamma),
+            _p(dres), ld_dres, _p(dx), ld_dx, _p(dbranch), _p(dgamma), _p(dbeta), rows, D,
+            float(dropout_p), int(seed), int(offset), _l.stream_ptr())
+    return dx, dbranch, dgamma, dbeta
+
+
+def attention_supported(Sq, Sk, d):
+    return bool(_l.lib().vitssl_attention_supported(Sq, Sk, d))
+
+
+def attention_fwd(q, k, v, H, scale, want_lse=True):
+    """q: bf16 [B,Sq,H*64] view (last dim contiguous, token pitch uniform); k,v likewise."""
+    _l.ensure_device()
+    B, Sq, _ = q.shape
+    Sk = k.shape[1]
+    for t_, S_ in ((q, Sq), (k, Sk), (v, Sk)):
+        assert t_.dtype == torch.bfloat16 and t_.stride(2) == 1 and t_.stride(0) == S_ * t_.stride(1)
+    out = torch.empty((B, Sq, H * 64), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32) if want_lse else None
+    _l.call("vitssl_attention_fwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), v.stride(1),
+            _p(out), out.stride(1), _p(lse), B, H, Sq, Sk, float(scale), _l.stream_ptr())
+    return out, lse
+
+
+def attention_bwd(q, k, v, out, d_out, lse, H, scale, dq, dk, dv):
+    """dq/dk/dv: preallocated bf16 [B,S,H*64] views (may alias slices of one [B,S,3D] buffer)."""
+    _l.ensure_device()
+    B, Sq, _ = q.shape
+    Sk = k.shape[1]
+    assert out.is_contiguous() and d_out.is_contiguous() and d_out.dtype == torch.bfloat16
+    _l.call("vitssl_attention_bwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), v.stride(1),
+            _p(out), _p(d_out), out.stride(1), _p(lse), _p(dq), dq.stride(1), _p(dk), dk.stride(1),
+            _p(dv), dv.stride(1), B, H, Sq, Sk, float(scale), _l.stream_ptr())
+
+
+def _strides_bhsd(t):
+    # t: [B,H,S,d] view with unit stride on d
+    assert t.stride(3) == 1
+    return [t.stride(0), t.stride(1), t.stride(2)]
+
+
+def attention_generic_fwd(q, k, v, scale, want_probs=False, want_lse=True):
+    """q,k,v: bf16 [B,H,S,d] views (any strides, unit stride on d). Returns (out [B,H,Sq,d], probs, lse)."""
+    import ctypes
+    _l.ensure_device()
+    B, H, Sq, d = q.shape
+    Sk = k.shape[2]
+    out = torch.empty((B, H, Sq, d), device=q.device, dtype=torch.bfloat16)
+    probs = torch.empty((B, H, Sq, Sk), device=q.device, dtype=torch.float32) if want_probs else None
+    lse = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32) if want_lse else None
+    st = _strides_bhsd(q) + _strides_bhsd(k) + _strides_bhsd(v) + _strides_bhsd(out)
+    arr = (ctypes.c_int64 * 12)(*st)
+    _l.call("vitssl_attention_generic_fwd", _p(q), _p(k), _p(v), ctypes.addressof(arr), _p(out),
+            _p(probs), _p(lse), B, H, Sq, Sk, d, float(scale), _l.stream_ptr())
+    return out, probs, lse
+
+
+def attention_generic_bwd(q, k, v, out, d_out, lse, scale):
+    """Returns (dq [B,H,Sq,d] bf16, dk, dv as fp32 [B,Sk,H,d])."""
+    import ctypes
+    _l.ensure_device()
+    B, H, Sq, d = q.shape
+    Sk = k.shape[2]
+    q = q.contiguous(); out = out.contiguous(); d_out = d_out.contiguous()
+    dq = torch.empty_like(q)
+    dk = torch.zeros((B, Sk, H, d), device=q.device, dtype=torch.float32)
+    dv = torch.zeros((B, Sk, H, d), device=q.device, dtype=torch.float32)
+    st = _strides_bhsd(q) + _strides_bhsd(k) + _strides_bhsd(v) + _strides_bhsd(out)
+    arr = (ctypes.c_int64 * 12)(*st)
+    _l.call("vitssl_attention_generic_bwd", _p(q), _p(k), _p(v), ctypes.addressof(arr), _p(out),
+            _p(d_out), _p(lse), _p(dq), _p(dk), _p(dv), B, H, Sq, Sk, d, float(scale),
+            _l.stream_ptr())
+    return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------
+# multi-tensor helpers
+# ----------------------------------------------------------------------------------------
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _numel_array(tensors):
+    import ctypes
+    return (ctypes.c_int64 * len(tensors))(*[t.numel() for t in tensors])
+
+
+def multi_cast_bf16(srcs, dsts):
+    """fp32 -> bf16 for lists of contiguous tensors (dst may be slices of a larger buffer)."""
+    import ctypes
+    if not srcs:
+        return
+    _l.ensure_device()
+    for s, d in zip(srcs, dsts):
+        assert s.dtype == torch.float32 and d.dtype == torch.bfloat16
+        assert s.is_contiguous() and d.is_contiguous() and s.numel() == d.numel()
+    a, b, n = _ptr_array(srcs), _ptr_array(dsts), _numel_array(srcs)
+    _l.call("vitssl_multi_cast_bf16", ctypes.addressof(a), ctypes.addressof(b), ctypes.addressof(n),
+            len(srcs), _l.stream_ptr())
+
+
+def cast_bf16(x):
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    multi_cast_bf16([x.contiguous()], [out])
+    return out
+
+
+def multi_ema(teacher, student, momentum):
+    import ctypes
+    if not teacher:
+        return
+    _l.ensure_device()
+    for t, s in zip(teacher, student):
+        assert t.dtype == torch.float32 and s.dtype == torch.float32
+        assert t.is_contiguous() and s.is_contiguous() and t.numel() == s.numel()
+    a, b, n = _ptr_array(teacher), _ptr_array(student), _numel_array(teacher)
+    _l.call("vitssl_multi_ema", ctypes.addressof(a), ctypes.addressof(b), ctypes.addressof(n),
+            len(teacher), float(momentum), _l.stream_ptr())
+
+
+def colsum_bf16(x):
+    """x: bf16 [rows, cols] (unit inner stride) -> fp32 [cols]."""
+    _l.ensure_device()
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty(x.shape[1], device=x.device, dtype=torch.float32)
+    _l.call("vitssl_colsum_bf16", _p(x), x.stride(0), x.shape[0], x.shape[1], _p(out), _l.stream_ptr())
+    return out
+
+
+def im2col_bf16(img, p):
+    _l.ensure_device()
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4
+    B, C, H, W = img.shape
+    out = torch.empty((B * (H // p) * (W // p), C * p * p), device=img.device, dtype=torch.bfloat16)
+    _l.call("vitssl_im2col_bf16", _p(img), _p(out), B, C, H, W, p, _l.stream_ptr())
+    return out
+
+
+def gather_patches_f32(img, rows_idx, p):
+    _l.ensure_device()
+    assert img.dtype == torch.float32 and img.is_contiguous() and rows_idx.dtype == torch.int32
+    B, C, H, W = img.shape
+    out = torch.empty((rows_idx.numel(), C * p * p), device=img.device, dtype=torch.float32)
+    _l.call("vitssl_gather_patches_f32", _p(img), _p(rows_idx), _p(out), rows_idx.numel(), C, H, W, p,
+            _l.stream_ptr())
+    return out
+
+
+def embed_tokens_fwd(proj, cls, pos, mask_u8, mask_token, B, N, D):
+    _l.ensure_device()
+    S = N + (1 if cls is not None else 0)
+    x = torch.empty((B, S, D), device=proj.device, dtype=torch.float32)
+    _l.call("vitssl_embed_tokens_fwd", _p(proj), _p(cls), _p(pos), _p(mask_u8), _p(mask_token), _p(x),
+            B, N, D, _l.stream_ptr())
+    return x
+
+
+def embed_tokens_bwd(dx, mask_u8, B, N, D, has_cls, want_dmask_token):
+    _l.ensure_device()
+    S = N + (1 if has_cls else 0)
+    assert dx.dtype == torch.float32 and dx.shape == (B, S, D) and dx.stride(2) == 1
+    dproj = torch.empty((B * N, D), device=dx.device, dtype=torch.bfloat16)
+    dpos = torch.empty((S, D), device=dx.device, dtype=torch.float32)
+    dmt = torch.empty(D, device=dx.device, dtype=torch.float32) if want_dmask_token else None
+    _l.call("vitssl_embed_tokens_bwd", _p(dx), dx.stride(0), dx.stride(1), _p(mask_u8), _p(dproj),
+            _p(dpos), _p(dmt), B, N, D, int(has_cls), _l.stream_ptr())
+    return dproj, dpos, dmt
+
+
+def gather_rows_bf16(x2d, idx):
+    _l.ensure_device()
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2 and x2d.stride(1) == 1 and idx.dtype == torch.int32
+    out = torch.empty((idx.numel(), x2d.shape[1]), device=x2d.device, dtype=torch.bfloat16)
+    _l.call("vitssl_gather_rows_bf16", _p(x2d), x2d.stride(0), _p(idx), _p(out), idx.numel(), x2d.shape[1],
+            _l.stream_ptr())
+    return out
+
+
+def scatter_rows_f32(dy, inv_idx, rows):
+    _l.ensure_device()
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and inv_idx.dtype == torch.int32
+    D = dy.shape[1]
+    dx = torch.empty((rows, D), device=dy.device, dtype=torch.float32)
+    _l.call("vitssl_scatter_rows_f32", _p(dy), _p(inv_idx), _p(dx), rows, D, _l.stream_ptr())
+    return dx
+
+
+def l1_loss_fwd(pred, target, want_sign=True):
+    _l.ensure_device()
+    assert pred.dtype == torch.bfloat16 and target.dtype == torch.float32
+    assert pred.is_contiguous() and target.is_contiguous() and pred.numel() == target.numel()
+    sign = torch.empty_like(pred) if want_sign else None
+    loss = torch.empty((), device=pred.device, dtype=torch.float32)
+    _l.call("vitssl_l1_loss_fwd", _p(pred), _p(target), _p(sign), _p(loss), pred.numel(), _l.stream_ptr())
+    return loss, sign
+
+
+def l2norm_fwd(x):
+    _l.ensure_device()
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 2
+    y = torch.empty_like(x)
+    inv = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+    _l.call("vitssl_l2norm_fwd", _p(x), _p(y), _p(inv), x.shape[0], x.shape[1], _l.stream_ptr())
+    return y, inv
+
+
+def l2norm_bwd(x, inv, dy):
+    _l.ensure_device()
+    dx = torch.empty_like(x)
+    _l.call("vitssl_l2norm_bwd", _p(x), _p(inv), _p(dy), _p(dx), x.shape[0], x.shape[1], _l.stream_ptr())
+    return dx
+
+
+def weight_norm_fwd(v, g, out=None):
+    _l.ensure_device()
+    assert v.dtype == torch.float32 and v.is_contiguous() and g.is_contiguous() and g.numel() == v.shape[0]
+    w = out if out is not None else torch.empty(v.shape, device=v.device, dtype=torch.bfloat16)
+    inv = torch.empty(v.shape[0], device=v.device, dtype=torch.float32)
+    _l.call("vitssl_weight_norm_fwd", _p(v), _p(g), _p(w), _p(inv), v.shape[0], v.shape[1], _l.stream_ptr())
+    return w, inv
+
+
+def weight_norm_bwd(dw, v, g, inv):
+    _l.ensure_device()
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    dg = torch.empty_like(g)
+    dv = torch.empty_like(v)
+    _l.call("vitssl_weight_norm_bwd", _p(dw), _p(v), _p(g), _p(inv), _p(dg), _p(dv), v.shape[0], v.shape[1],
+            _l.stream_ptr())
+    return dg, dv
+
+
+def center_ema(center, colsum, momentum, inv_rows):
+    _l.ensure_device()
+    out = torch.empty_like(center)
+    _l.call("vitssl_center_ema", _p(center), _p(colsum), _p(out), center.numel(), float(momentum),
+            float(inv_rows), _l.stream_ptr())
+    return out
+
+
+def dino_loss_fwd(teacher, student, center, teacher_temp, student_temp):
+    _l.ensure_device()
+    G, B, K = teacher.shape
+    V = student.shape[0]
+    assert teacher.dtype == torch.bfloat16 and student.dtype == torch.bfloat16
+    assert teacher.is_contiguous() and student.is_contiguous() and center.dtype == torch.float32
+    loss = torch.empty((), device=teacher.device, dtype=torch.float32)
+    t_stats = torch.empty((G, B, 2), device=teacher.device, dtype=torch.float32)
+    s_lse = torch.empty((V, B), device=teacher.device, dtype=torch.float32)
+    _l.call("vitssl_dino_loss_fwd", _p(teacher), _p(student), _p(center), _p(loss), _p(t_stats), _p(s_lse),
+            G, V, B, K, float(teacher_temp), float(student_temp), _l.stream_ptr())
+    return loss, t_stats, s_lse
+
+
+def dino_loss_bwd(teacher, student, center, t_stats, s_lse, grad_out, teacher_temp, student_temp):
+    _l.ensure_device()
+    G, B, K = teacher.shape
+    V = student.shape[0]
+    dstudent = torch.empty_like(student)
+    go = grad_out.reshape(()).to(torch.float32).contiguous()
+    _l.call("vitssl_dino_loss_bwd", _p(teacher), _p(student), _p(center), _p(t_stats), _p(s_lse), _p(go),
+            _p(dstudent), G, V, B, K, float(teacher_temp), float(student_temp), _l.stream_ptr())
+    return dstudent
