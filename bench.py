@@ -235,7 +235,7 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # ---- timed region 2: end to end (pinned host -> device each step, loss read back) ----
     copy_stream = torch.cuda.Stream()
@@ -275,7 +275,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         recs, ops.PROFILE = ops.PROFILE, None
         pk = peaks()
-        gemm = [(a.elapsed_time(b), w) for (k, a, b, w) in recs if k == "gemm"]
+        gemm = [(a.elapsed_time(b), w) for (k, a, b, w) in recs if k.startswith("gemm")]
         ln = [(a.elapsed_time(b), w) for (k, a, b, w) in recs if k == "add_layernorm"]
         if gemm:
             t = sum(x for x, _ in gemm); f = sum(w for _, w in gemm)

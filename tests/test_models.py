@@ -40,11 +40,12 @@ def check_grads(module, golden_grads, yard=None, tol=GRAD_TOL):
         if k not in golden_grads:
             continue
         assert p.grad is not None, k
-        assert rel_l2(p.grad, golden_grads[k]) <= tol, (k, "rel-L2", rel_l2(p.grad, golden_grads[k]))
-        e = rel(p.grad, golden_grads[k])
-        allowed = tol
+        e2, e = rel_l2(p.grad, golden_grads[k]), rel(p.grad, golden_grads[k])
+        allowed2 = allowed = tol
         if yard is not None and k in yard:
+            allowed2 = max(tol, 2.0 * rel_l2(yard[k], golden_grads[k]))
             allowed = max(tol, 2.0 * rel(yard[k], golden_grads[k]))
+        assert e2 <= allowed2, (k, "rel-L2", e2, "allowed", allowed2)
         assert e <= allowed, (k, "max-rel", e, "allowed", allowed)
         if e > worst[1]:
             worst = (k, e, allowed)
@@ -199,8 +200,8 @@ def test_simmim_mask_is_the_reference_rng_sequence():
     assert torch.equal(bool_mask.cpu(), vit_ref.mask_from_perms(perms, N, r))
     assert torch.equal(rows.cpu().long(), bool_mask.reshape(-1).nonzero().squeeze(1).cpu())
     assert torch.equal((inv >= 0).cpu(), bool_mask.reshape(-1).cpu())
-    torch.cuda.set_rng_state(state)
     patches = torch.rand(B, N, 48, device="cuda")
+    torch.cuda.set_rng_state(state)
     _, bm, tg = simple_masking(patches, r)
     assert torch.equal(bm, bool_mask) and torch.equal(tg, patches[bm])
 
@@ -225,7 +226,7 @@ def test_dino_forward_loss_backward_ema():
     for k, p in m.named_parameters():
         if k in g["grad_digests"]:
             dg = g["grad_digests"][k]
-            mine = digest(p.grad)
+            mine = digest(p.grad.cpu())
             e = ((mine["sample"] - dg["sample"]).abs().max() / dg["sample"].abs().max().clamp_min(1e-30)).item()
             en = abs(mine["norm"] - dg["norm"]) / max(dg["norm"], 1e-30)
             if max(e, en) > worst[1]:
@@ -236,7 +237,7 @@ def test_dino_forward_loss_backward_ema():
     m.momentum_update_teacher(g["momentum"])
     sd = m.state_dict()
     for k, dg in g["teacher_after_digests"].items():
-        e = (digest(sd[k])["sample"] - dg["sample"]).abs().max().item()
+        e = (digest(sd[k].cpu())["sample"] - dg["sample"]).abs().max().item()
         assert e <= 1e-6 * max(1.0, dg["sample"].abs().max().item()), k
     feats = m.inference_forward(views[0].cuda())
     assert not m.training and feats.shape == (B, 512)
@@ -247,13 +248,17 @@ def test_dino_loss_kernel_matches_reference_and_closed_form():
     g = load("dino_loss")
     s = g["student"].cuda().requires_grad_(True)
     loss = DINOLoss(*g["temps"])(g["teacher"].cuda(), s, g["center"].cuda())
-    # bf16 logits: compare against the oracle evaluated on the bf16-rounded inputs as well
-    tb, sb = g["teacher"].bfloat16().double(), g["student"].bfloat16().double()
+    # the kernels read bf16 logits: the oracle on the same bf16-rounded inputs is the tight check,
+    # the golden value (fp32 inputs through the real reference) the loose one
+    tb = g["teacher"].bfloat16().double()
+    sb = g["student"].bfloat16().double().requires_grad_(True)
     ref_b = vit_ref.dino_loss(tb, sb, g["center"].double(), *g["temps"])
-    assert abs(loss.item() - ref_b.item()) <= LOSS_TOL * abs(ref_b.item())
+    ref_b.backward()
+    assert abs(loss.item() - ref_b.item()) <= 1e-4 * abs(ref_b.item())
     assert abs(loss.item() - g["loss"].item()) <= 5e-3 * abs(g["loss"].item())
     (loss * 65536.0).backward()  # GradScaler-style scaled backward
-    assert rel(s.grad / 65536.0, g["dstudent"]) <= 3e-2
+    assert rel(s.grad / 65536.0, sb.grad) <= 1e-2
+    assert rel_l2(s.grad / 65536.0, sb.grad) <= 1e-2
 
 
 def test_no_cpu_fallback():

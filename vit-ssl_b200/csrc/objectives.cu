@@ -173,7 +173,8 @@ __global__ void center_ema_kernel(const float* __restrict__ center, const float*
 
 // ---------------------------------------------------------------------------------------
 // DINO loss, factorised:  L = -(1/(G B K)) sum_b [ sum_g N_g / Z_g  -  G * sum_v lse_v ]
-//   a_gk = (t_gk - c_k)/tau_t,  X_k = sum_v s'_vk,  s'_vk = bf16(s_vk / tau_s)  (loss.py:23)
+//   a_gk = (t_gk - c_k)/tau_t,  X_k = sum_v s'_vk,  s'_vk = s_vk / tau_s in fp32 (loss.py:23; the
+//   reference under autocast rounds s/tau_s to bf16 first — we keep fp32, which is closer to its fp32 math)
 //   N_g = sum_k exp(a_gk - m_g) X_k,  Z_g = sum_k exp(a_gk - m_g),  lse_v = logsumexp_k s'_vk
 // One CTA per batch sample streams its G + V rows once with online (max, sum) rescaling.
 // ---------------------------------------------------------------------------------------
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(DL_THREADS) dino_loss_fwd_kernel(const DinoLos
       unpack8(*reinterpret_cast<const uint4*>(a.student + (static_cast<long long>(v) * a.B + b) * a.K + k), s);
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] = bf16_round(s[j] * a.inv_ts); mx = fmaxf(mx, s[j]); x[j] += s[j]; }
+      for (int j = 0; j < 8; ++j) { s[j] = s[j] * a.inv_ts; mx = fmaxf(mx, s[j]); x[j] += s[j]; }
       const float mn = fmaxf(sm[v], mx);
       float acc = 0.f;
 #pragma unroll
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(256) dino_loss_bwd_kernel(const DinoLossBwdArg
     float d[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      d[j] = coef * (pbar[j] - static_cast<float>(G) * __expf(bf16_round(s[j] * a.inv_ts) - lse));
+      d[j] = coef * (pbar[j] - static_cast<float>(G) * __expf(s[j] * a.inv_ts - lse));
     uint4 o;
     o.x = pack_bf16(d[0], d[1]); o.y = pack_bf16(d[2], d[3]); o.z = pack_bf16(d[4], d[5]); o.w = pack_bf16(d[6], d[7]);
     *reinterpret_cast<uint4*>(a.dstudent + off) = o;

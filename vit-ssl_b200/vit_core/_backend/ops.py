@@ -81,7 +81,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_NONE, bias=None, aux=None
         float(alpha), int(out_dtype == torch.float32), int(split_k), float(dropout_p),
         int(seed), int(offset), _l.stream_ptr(),
     )
-    _prof_end("gemm", e0, 2.0 * M * N * K)
+    _prof_end(f"gemm|{M}x{N}x{K}|a_mn={int(a_mn)} b_mn={int(b_mn)} epi={int(epilogue)}", e0, 2.0 * M * N * K)
     return out
 
 
