@@ -56,8 +56,22 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
+static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                             uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer,
+                             CUtensorMapSwizzle swz);
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_2d_impl(out, base, inner, outer, ld_bytes, box_inner, box_outer, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int make_tmap_bf16_2d_sw64(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                           uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_2d_impl(out, base, inner, outer, ld_bytes, box_inner, box_outer, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                             uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer,
+                             CUtensorMapSwizzle swz) {
   auto fn = encode_fn();
   VITSSL_REQUIRE(fn != nullptr, VITSSL_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {inner, outer};
@@ -65,7 +79,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VITSSL_REQUIRE(r == CUDA_SUCCESS, VITSSL_ERR_CUDA,
                  "cuTensorMapEncodeTiled(2d) failed: %d (inner %llu outer %llu pitch %llu box %u x %u)",

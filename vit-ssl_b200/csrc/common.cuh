@@ -175,6 +175,25 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA store: shared memory tile -> global (clipped at the tensor bounds), bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {  // smem of all but the N newest groups is reusable
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------
@@ -270,6 +289,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool a_mn, 
 // 2-D bf16 tensor [outer][inner] with row pitch ld_bytes; 128B-swizzled box.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer);
+// same with 64-byte swizzle (32 bf16 wide boxes; used by the GEMM epilogue's TMA stores)
+int make_tmap_bf16_2d_sw64(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                           uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer);
 // 3-D bf16 tensor [d2][d1][inner]
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2,
                       uint64_t ld1_bytes, uint64_t ld2_bytes, uint32_t box_inner, uint32_t box_d1,
