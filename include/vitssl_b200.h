@@ -143,6 +143,23 @@ int vitssl_gather_rows_bf16(const float* x, int64_t ldx, const int32_t* idx, voi
 int vitssl_scatter_rows_f32(const void* dy, const int32_t* inv_idx, float* dx, int64_t rows,
                             int64_t D, vitssl_stream_t stream);
 
+/* ---- SimMIM masking (ssl/simmim/masking.py:6-37) ------------------------------------------ */
+/* Bit-exact replay of B sequential `torch.randperm(N, device=cuda)[:n_keep]` draws from the
+ * Philox state (seed, offset) of torch's CUDA generator, fused with the mask bookkeeping:
+ *   perm_out  int64 [B, n_keep] (nullable)  the drawn indices, in draw order (masking.py:22-25)
+ *   bool_mask uint8 [B, N]                   1 where masked (masking.py:27-33)
+ *   rows      int32 [B*n_keep]               flat ids b*N+n of masked patches, ascending — the
+ *                                            row order of `patches[bool_mask]` (masking.py:35)
+ *   inv       int32 [B*N]                    position of a patch in `rows`, or -1
+ * N <= 1024. The caller must advance the generator offset by
+ * B * vitssl_randperm_offset_per_call(N) so later draws continue the reference's stream. */
+int vitssl_simmim_mask(int64_t* perm_out, uint8_t* bool_mask, int32_t* rows, int32_t* inv,
+                       int64_t B, int64_t N, int64_t n_keep, uint64_t philox_seed,
+                       uint64_t philox_offset, vitssl_stream_t stream);
+/* key width torch.randperm uses for n elements, and the generator offset one call consumes */
+int vitssl_randperm_bits(int64_t n);
+int64_t vitssl_randperm_offset_per_call(int64_t n);
+
 /* ---- SimMIM objective --------------------------------------------------------------------- */
 /* loss[0] = mean |pred - target| (nn.L1Loss(mean): utils/train_utils.py:19-22); sign (bf16,
  * nullable) receives sign(pred - target) so that d(pred) = sign * grad / n needs no second read

@@ -159,7 +159,8 @@ def _simmim(g):
 def test_simmim_forward_backward(monkeypatch):
     g = load("simmim")
     m, mod, idx = _simmim(g)
-    monkeypatch.setattr(mod, "draw_mask_indices", lambda B, N, r, dev: idx)
+    from vit_core.ssl.simmim.masking import mask_tables
+    monkeypatch.setattr(mod, "draw_mask", lambda B, N, r, dev, want_indices=True: (idx, *mask_tables(idx, N)))
     pred, targets, bool_mask = m(g["x"].cuda(), return_bool_mask=True)
     assert torch.equal(bool_mask.squeeze(-1).cpu(), g["bool_mask"])          # mask bit-exact
     assert torch.equal(targets.cpu().double(), g["targets"])                 # raw pixels bit-exact
@@ -185,25 +186,48 @@ def test_simmim_forward_backward(monkeypatch):
 
 
 def test_simmim_mask_is_the_reference_rng_sequence():
-    """masking.py:22-25 draws B sequential torch.randperm(N, device)[:n_m]; replaying the device
-    generator must reproduce our mask bit for bit, and the derived tables must match the oracle."""
-    from vit_core.ssl.simmim.masking import draw_mask_indices, mask_tables, simple_masking
-    torch.manual_seed(1234)
-    B, N, r = 7, 196, 0.6
+    """masking.py:22-25 draws B sequential torch.randperm(N, device)[:n_m]; our one-launch replay of
+    that integer algorithm must reproduce torch's own draws bit for bit from the same generator
+    state, leave the generator where the B calls would, and emit the oracle's mask tables."""
+    from vit_core.ssl.simmim.masking import draw_mask, draw_mask_indices, mask_tables, simple_masking
+    dev = torch.device("cuda")
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    # (B, N, ratio): BASELINE shapes (196, 36), the shipped 144, edge sizes, > 256 (second key block)
+    cases = [(7, 196, 0.6), (256, 196, 0.6), (64, 36, 0.6), (33, 144, 0.75), (5, 1, 0.6), (9, 2, 0.5),
+             (4, 257, 0.6), (3, 576, 0.6), (2, 1024, 0.9), (300, 64, 1.0), (6, 49, 0.0)]
+    for seed, (B, N, r) in enumerate(cases):
+        torch.manual_seed(1234 + seed)
+        torch.rand(3, device="cuda")                      # move the offset off zero
+        state = torch.cuda.get_rng_state()
+        n_m = int(N * r)
+        ref = torch.stack([torch.randperm(N, device="cuda")[:n_m] for _ in range(B)])
+        off_ref = gen.get_offset()
+        after_ref = torch.rand(4, device="cuda")
+        torch.cuda.set_rng_state(state)
+        ours, bool_mask, rows, inv = draw_mask(B, N, r, dev)
+        assert gen.get_offset() == off_ref, (B, N, gen.get_offset(), off_ref)
+        assert torch.equal(torch.rand(4, device="cuda"), after_ref)   # later draws continue the same stream
+        assert ours.dtype == torch.int64 and torch.equal(ours, ref), (B, N, r)
+        bm2, rows2, inv2 = mask_tables(ref, N)
+        assert torch.equal(bool_mask, bm2) and torch.equal(rows, rows2) and torch.equal(inv, inv2), (B, N, r)
+        perms = torch.cat([ours.cpu(), torch.zeros(B, N - n_m, dtype=torch.long)], dim=1)
+        assert torch.equal(bool_mask.cpu(), vit_ref.mask_from_perms(perms, N, r))
+        assert torch.equal(rows.cpu().long(), bool_mask.reshape(-1).nonzero().squeeze(1).cpu())
+    # duplicate 18-bit keys (islands) do occur at these sizes: 4096 samples of N=196 hold ~300 of them
+    torch.manual_seed(99)
     state = torch.cuda.get_rng_state()
-    ours = draw_mask_indices(B, N, r, torch.device("cuda"))
+    ref = torch.stack([torch.randperm(196, device="cuda") for _ in range(4096)])
     torch.cuda.set_rng_state(state)
-    ref = torch.stack([torch.randperm(N, device="cuda")[: int(N * r)] for _ in range(B)])
+    ours = draw_mask_indices(4096, 196, 1.0, dev)
     assert torch.equal(ours, ref)
-    bool_mask, rows, inv = mask_tables(ours, N)
-    perms = torch.cat([ours.cpu(), torch.zeros(B, N - ours.shape[1], dtype=torch.long)], dim=1)
-    assert torch.equal(bool_mask.cpu(), vit_ref.mask_from_perms(perms, N, r))
-    assert torch.equal(rows.cpu().long(), bool_mask.reshape(-1).nonzero().squeeze(1).cpu())
-    assert torch.equal((inv >= 0).cpu(), bool_mask.reshape(-1).cpu())
+    # the reference-shaped helper
+    B, N, r = 7, 196, 0.6
     patches = torch.rand(B, N, 48, device="cuda")
+    state = torch.cuda.get_rng_state()
+    ref = torch.stack([torch.randperm(N, device="cuda")[: int(N * r)] for _ in range(B)])
     torch.cuda.set_rng_state(state)
     _, bm, tg = simple_masking(patches, r)
-    assert torch.equal(bm, bool_mask) and torch.equal(tg, patches[bm])
+    assert torch.equal(bm, mask_tables(ref, N)[0]) and torch.equal(tg, patches[bm])
 
 
 def test_dino_forward_loss_backward_ema():

@@ -150,3 +150,23 @@ def test_schedulers_match_reference_formulae():
         assert ms.get_momentum(step) == pytest.approx(vit_ref.momentum_schedule(0.996, 1.0, 50, step), abs=1e-15)
         assert ts_c.get_temp(step) == pytest.approx(vit_ref.teacher_temp_schedule(0.04, 0.07, 30, step), abs=1e-15)
         assert ts_l.get_temp(step) == pytest.approx(vit_ref.teacher_temp_schedule(0.04, 0.07, 30, step, "linear"), abs=1e-15)
+
+
+def test_randperm_oracle_matches_torch_cuda_draws():
+    """oracle/randperm_ref.py (numpy restatement of torch.randperm on CUDA, which defines the SimMIM
+    mask: masking.py:22-25) against permutations torch itself drew on a B200
+    (tests/golden/randperm_cuda.pt, made by oracle/make_randperm_golden.py)."""
+    import numpy as np
+    from oracle import randperm_ref as R
+    g = torch.load(os.path.join(GOLD, "randperm_cuda.pt"), weights_only=False)
+    assert len(g["cases"]) >= 9
+    for c in g["cases"]:
+        off = c["offset"]
+        for r in range(min(c["reps"], 48)):
+            perm, off = R.cuda_randperm(c["n"], c["seed"], off)
+            assert np.array_equal(perm, c["perms"][r].numpy().astype(np.int64)), (c["n"], c["seed"], r)
+        if c["reps"] <= 48:
+            assert off == c["offset_after"]
+        assert c["offset"] + c["reps"] * R.offset_per_call(c["n"]) == c["offset_after"]
+    idx, off = R.simmim_mask_indices(3, 196, 117, 42, 0)
+    assert np.array_equal(idx, g["cases"][0]["perms"][:3, :117].numpy()) and off == 600

@@ -44,6 +44,7 @@ SIGNATURES["vitssl_embed_tokens_fwd"] = "pppppp" + "lll" + "s"
 SIGNATURES["vitssl_embed_tokens_bwd"] = "pllp" + "ppp" + "lll" + "i" + "s"
 SIGNATURES["vitssl_gather_rows_bf16"] = "plppll" + "s"
 SIGNATURES["vitssl_scatter_rows_f32"] = "pppll" + "s"
+SIGNATURES["vitssl_simmim_mask"] = "pppp" + "lll" + "uu" + "s"
 SIGNATURES["vitssl_l1_loss_fwd"] = "ppppl" + "s"
 SIGNATURES["vitssl_l2norm_fwd"] = "pppll" + "s"
 SIGNATURES["vitssl_l2norm_bwd"] = "ppppll" + "s"
@@ -76,6 +77,10 @@ def _load():
     lib.vitssl_num_sms.restype = ctypes.c_int
     lib.vitssl_launch_count.restype = ctypes.c_int64
     lib.vitssl_launch_count.argtypes = [ctypes.c_int]
+    lib.vitssl_randperm_bits.restype = ctypes.c_int
+    lib.vitssl_randperm_bits.argtypes = [ctypes.c_int64]
+    lib.vitssl_randperm_offset_per_call.restype = ctypes.c_int64
+    lib.vitssl_randperm_offset_per_call.argtypes = [ctypes.c_int64]
     for name, sig in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int

@@ -296,6 +296,34 @@ def gather_patches_f32(img, rows_idx, p):
     return out
 
 
+RANDPERM_MAX_N = 1024
+
+
+def randperm_offset_per_call(n: int) -> int:
+    """Philox offset one `torch.randperm(n, device=cuda)` call consumes (Randperm.cu)."""
+    return int(_l.lib().vitssl_randperm_offset_per_call(int(n)))
+
+
+def simmim_mask(B, N, n_keep, device, want_perm=True):
+    """B sequential `torch.randperm(N, device=cuda)[:n_keep]` draws replayed bit-exactly in one
+    launch from the device's default generator, which is advanced exactly as those calls would
+    (ssl/simmim/masking.py:22-25). Returns (perm int64 [B,n_keep] | None, bool_mask [B,N],
+    rows int32 [B*n_keep], inv int32 [B*N])."""
+    _l.ensure_device()
+    dev = torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[index]
+    seed, offset = int(gen.initial_seed()), int(gen.get_offset())
+    gen.set_offset(offset + B * randperm_offset_per_call(N))
+    perm = torch.empty((B, n_keep), device=dev, dtype=torch.int64) if want_perm else None
+    bool_mask = torch.empty((B, N), device=dev, dtype=torch.bool)
+    rows = torch.empty((B * n_keep,), device=dev, dtype=torch.int32)
+    inv = torch.empty((B * N,), device=dev, dtype=torch.int32)
+    _l.call("vitssl_simmim_mask", _p(perm), _p(bool_mask), _p(rows), _p(inv), B, N, n_keep,
+            seed & 0xFFFFFFFFFFFFFFFF, offset, _l.stream_ptr())
+    return perm, bool_mask, rows, inv
+
+
 def embed_tokens_fwd(proj, cls, pos, mask_u8, mask_token, B, N, D):
     _l.ensure_device()
     S = N + (1 if cls is not None else 0)

@@ -9,7 +9,7 @@ from torch import nn
 
 from .._backend_access import Fb, ops
 from ...encoder_block import EncoderBlock
-from .masking import draw_mask_indices, mask_tables
+from .masking import draw_mask
 
 
 class SimMIMViT(nn.Module):
@@ -33,8 +33,7 @@ class SimMIMViT(nn.Module):
         B, C, H, W = x.shape
         p = self.patch_size
         N = (H // p) * (W // p)
-        idx = draw_mask_indices(B, N, self.mask_ratio, x.device)
-        bool_mask, rows, inv = mask_tables(idx, N)
+        _, bool_mask, rows, inv = draw_mask(B, N, self.mask_ratio, x.device, want_indices=False)
         x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
         targets = ops.gather_patches_f32(x, rows, p)
         tokens = Fb.embed_patches(x, self, self.projection.weight, self.projection.bias, None,
