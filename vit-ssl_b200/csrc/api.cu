@@ -56,36 +56,32 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
-static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                             uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer,
-                             CUtensorMapSwizzle swz);
-
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                      uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer) {
-  return make_tmap_2d_impl(out, base, inner, outer, ld_bytes, box_inner, box_outer, CU_TENSOR_MAP_SWIZZLE_128B);
-}
-int make_tmap_bf16_2d_sw64(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                           uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer) {
-  return make_tmap_2d_impl(out, base, inner, outer, ld_bytes, box_inner, box_outer, CU_TENSOR_MAP_SWIZZLE_64B);
-}
-
-static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                             uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer,
-                             CUtensorMapSwizzle swz) {
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                 uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   auto fn = encode_fn();
   VITSSL_REQUIRE(fn != nullptr, VITSSL_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  VITSSL_REQUIRE(elem_bytes == 2 || elem_bytes == 4, VITSSL_ERR_ARG, "tmap: element size %d", elem_bytes);
+  const CUtensorMapSwizzle swz = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                       : CU_TENSOR_MAP_SWIZZLE_NONE;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VITSSL_REQUIRE(r == CUDA_SUCCESS, VITSSL_ERR_CUDA,
                  "cuTensorMapEncodeTiled(2d) failed: %d (inner %llu outer %llu pitch %llu box %u x %u)",
                  (int)r, (unsigned long long)inner, (unsigned long long)outer,
                  (unsigned long long)ld_bytes, box_inner, box_outer);
   return VITSSL_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_2d(out, base, 2, inner, outer, ld_bytes, box_inner, box_outer, 128);
 }
 
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2,

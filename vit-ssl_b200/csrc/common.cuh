@@ -75,14 +75,18 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // ----------------------------------------------------------------------------------
-// Philox4x32-10 (counter-based; one 128-bit draw per (seed, offset, index))
+// Philox4x32 (counter-based; one 128-bit draw per (seed, offset, index)). 10 rounds is the
+// curand-compatible generator (masking.cu replays torch's streams with it); the dropout masks
+// use the 7-round variant (the shortest Crush-resistant one), they only have to be reproducible
+// between forward and backward.
 // ----------------------------------------------------------------------------------
+template <int ROUNDS = 10>
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint64_t index) {
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   uint32_t c0 = static_cast<uint32_t>(index), c1 = static_cast<uint32_t>(index >> 32);
   uint32_t c2 = static_cast<uint32_t>(offset), c3 = static_cast<uint32_t>(offset >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
@@ -91,11 +95,13 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// keep-mask bit for element `e` of a dropout site: 16-bit lanes of one Philox draw
-// cover 8 consecutive elements; keep iff u16 >= thresh16 (thresh16 = p * 65536).
+constexpr int DROPOUT_PHILOX_ROUNDS = 7;
+// Dropout of element e: the 16-bit lanes of one Philox draw cover 8 consecutive elements
+// (draw index = e / 8, lane = e % 8 counted from the low half of .x); keep iff u16 >= thresh16
+// (thresh16 = p * 65536). Both forms below implement exactly this rule.
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t group8,
                                                   uint32_t thresh16) {
-  const uint4 r = philox4x32(seed, offset, group8);
+  const uint4 r = philox4x32<DROPOUT_PHILOX_ROUNDS>(seed, offset, group8);
   uint32_t m = 0;
   m |= ((r.x & 0xffffu) >= thresh16) << 0;
   m |= ((r.x >> 16) >= thresh16) << 1;
@@ -106,6 +112,66 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset
   m |= ((r.w & 0xffffu) >= thresh16) << 6;
   m |= ((r.w >> 16) >= thresh16) << 7;
   return m;
+}
+// same rule as per-element multipliers: m[i] = keep ? scale : 0 (the 16-bit compares are done
+// in place on the 32-bit words: hi >= t <=> word >= t << 16; lo >= t <=> word << 16 >= t << 16)
+__device__ __forceinline__ void dropout_scale8(uint64_t seed, uint64_t offset, uint64_t group8,
+                                               uint32_t thresh16, float scale, float (&m)[8]) {
+  const uint4 r = philox4x32<DROPOUT_PHILOX_ROUNDS>(seed, offset, group8);
+  const uint32_t th = thresh16 << 16;
+  m[0] = ((r.x << 16) >= th) ? scale : 0.0f;
+  m[1] = (r.x >= th) ? scale : 0.0f;
+  m[2] = ((r.y << 16) >= th) ? scale : 0.0f;
+  m[3] = (r.y >= th) ? scale : 0.0f;
+  m[4] = ((r.z << 16) >= th) ? scale : 0.0f;
+  m[5] = (r.z >= th) ? scale : 0.0f;
+  m[6] = ((r.w << 16) >= th) ? scale : 0.0f;
+  m[7] = (r.w >= th) ? scale : 0.0f;
+}
+
+// ----------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2): two lanes per issue slot
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// standard normal cdf of two values: Phi(x) = 0.5 + t * Q(t^2), t = clamp(x, +-4.2), Q the
+// degree-8 minimax polynomial (|error| <= 1.1e-5 over the whole real line, fp32 evaluation).
+// No MUFU, 10 packed FMAs per pair. GELU(x) = x * Phi(x) (feed_forward.py:26, exact-erf GELU).
+__device__ __forceinline__ f32x2 normal_cdf2(float x0, float x1) {
+  const float t0 = fminf(fmaxf(x0, -4.2f), 4.2f), t1 = fminf(fmaxf(x1, -4.2f), 4.2f);
+  const f32x2 t = pk2(t0, t1);
+  const f32x2 s = fmul2(t, t);
+  f32x2 q = ffma2(s, pk2(5.994787999e-11f, 5.994787999e-11f), pk2(-5.630807376e-09f, -5.630807376e-09f));
+  q = ffma2(s, q, pk2(2.342876257e-07f, 2.342876257e-07f));
+  q = ffma2(s, q, pk2(-5.759411124e-06f, -5.759411124e-06f));
+  q = ffma2(s, q, pk2(9.456112457e-05f, 9.456112457e-05f));
+  q = ffma2(s, q, pk2(-1.114074141e-03f, -1.114074141e-03f));
+  q = ffma2(s, q, pk2(9.829915129e-03f, 9.829915129e-03f));
+  q = ffma2(s, q, pk2(-6.636010855e-02f, -6.636010855e-02f));
+  q = ffma2(s, q, pk2(3.989073634e-01f, 3.989073634e-01f));
+  return ffma2(t, q, pk2(0.5f, 0.5f));
 }
 
 // ----------------------------------------------------------------------------------
@@ -289,9 +355,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool a_mn, 
 // 2-D bf16 tensor [outer][inner] with row pitch ld_bytes; 128B-swizzled box.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer);
-// same with 64-byte swizzle (32 bf16 wide boxes; used by the GEMM epilogue's TMA stores)
-int make_tmap_bf16_2d_sw64(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                           uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer);
+// general 2-D map: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 0/32/64/128
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                 uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 // 3-D bf16 tensor [d2][d1][inner]
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2,
                       uint64_t ld1_bytes, uint64_t ld2_bytes, uint32_t box_inner, uint32_t box_d1,

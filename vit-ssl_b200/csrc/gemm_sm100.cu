@@ -1,13 +1,24 @@
 // vitssl_b200 — bf16 GEMM for sm_100a: TMA -> shared-memory ring -> tcgen05.mma -> TMEM ->
-// fused epilogue. One persistent, warp-specialised kernel serves every linear layer on the
-// hot path (reference call sites: attention.py:82-84,105; feed_forward.py:26-28;
-// patch_embedding.py:22,79-84,113-116; ssl/simmim/model.py:45,57; ssl/dino/head.py:10-17):
+// fused epilogue -> swizzled shared-memory staging -> TMA store. One persistent, warp-specialised
+// kernel serves every linear layer on the hot path (reference call sites: attention.py:82-84,105;
+// feed_forward.py:26-28; patch_embedding.py:22,79-84,113-116; ssl/simmim/model.py:45,57;
+// ssl/dino/head.py:10-17):
 //   forward   C[M,N]  = A[M,K] * W[N,K]^T      (both operands K-major)
 //   dgrad     dX[M,K] = dY[M,N] * W[N,K]       (B operand MN-major)
 //   wgrad     dW[N,K] = dY[M,N]^T * X[M,K]     (both operands MN-major, split-K + fp32 red)
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner,
-// warps 2-5 = epilogue (one TMEM lane quadrant each). Accumulators are double-buffered in
-// TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner,
+// warps 2-9 = epilogue (two per TMEM lane quadrant, half of the tile's columns each, so every
+// SM sub-partition has two warps to hide the epilogue's arithmetic latency). Accumulators are
+// double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1. Each epilogue
+// warp drains its 32 rows in 32-column chunks: tcgen05.ld (software-pipelined one chunk ahead) -> bias / GELU /
+// dGELU / dropout in registers -> 16-byte st.shared into a private, double-buffered staging tile
+// laid out in the TMA swizzle (bank-conflict free) -> one elected lane issues the bulk tensor
+// store, so global writes are full 64/128-byte row segments instead of per-thread row fragments.
+// The dGELU epilogue's pre-activation tile arrives the same way in reverse (TMA load, one chunk
+// ahead). Tiles whose output cannot be a TMA target (row pitch not a multiple of 16 bytes) and
+// split-K partial sums use the direct register->global epilogue.
+#include <string.h>
+
 #include "common.cuh"
 #include "vitssl_b200.h"
 
@@ -17,8 +28,12 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int STG_BUF_BYTES = 4096;                       // one 32x32 fp32 chunk, or bf16 C + bf16 aux
+constexpr int STG_BYTES = EPI_WARPS * 2 * STG_BUF_BYTES;  // double-buffered per epilogue warp
+constexpr int SMEM_LIMIT = 232448;                        // 227 KB per CTA
 
 struct GemmShape {
   int M, N, K;
@@ -36,7 +51,8 @@ struct GemmEpi {
   int mode;      // VITSSL_EPI_*
   int out_fp32;  // 1: fp32 output, 0: bf16
   int atomic;    // 1: red.add.f32 into C (split-K)
-  int vec_ok;    // C / aux rows are 16-byte aligned -> vector stores
+  int vec_ok;    // C rows are 16-byte aligned -> vector stores in the direct epilogue
+  int tma_out;   // 1: epilogue goes through staging + TMA store (tmap_c / tmap_aux valid)
   uint32_t drop_thresh16;
   float drop_scale;
   unsigned long long seed, offset;
@@ -44,32 +60,341 @@ struct GemmEpi {
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 5 : (BN == 128) ? 6 : 8;
   static constexpr int kBBytes = BN * BLOCK_K * 2;
   static constexpr int kStageBytes = A_TILE_BYTES + kBBytes;
+  static constexpr int kMaxStages = (SMEM_LIMIT - 1024 /*align*/ - 512 /*barriers*/ - STG_BYTES) / kStageBytes;
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + STG_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
-// Abramowitz-Stegun 7.1.26 erfc core: for z >= 0, erfc(z) = poly(t) * exp(-z^2), |err| < 1.5e-7.
-// Returns the standard normal cdf Phi(x) = 0.5 * erfc(-x / sqrt(2)) and w = exp(-x^2 / 2).
-__device__ __forceinline__ float normal_cdf_fast(float x, float& w) {
-  const float az = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  w = __expf(-az * az);
-  const float half_erfc = 0.5f * poly * w;
-  return x < 0.0f ? half_erfc : 1.0f - half_erfc;
+// ---- epilogue math on one 32-column chunk of one accumulator row (all in registers) ----------
+// fp32 output (NONE / BIAS): v[] <- alpha * acc (+ bias)
+template <int MODE>
+__device__ __forceinline__ void epilogue_math_f32(float (&v)[32], const GemmEpi& e, int nb, int ncols) {
+  float b[32];
+  if constexpr (MODE == VITSSL_EPI_BIAS) {
+    if (ncols == 32) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + nb + i));
+        b[i] = t.x; b[i + 1] = t.y; b[i + 2] = t.z; b[i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) b[i] = (i < ncols) ? __ldg(e.bias + nb + i) : 0.0f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = 0.0f;
+  }
+  const f32x2 al = pk2(e.alpha, e.alpha);
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) upk2(ffma2(pk2(v[i], v[i + 1]), al, pk2(b[i], b[i + 1])), v[i], v[i + 1]);
+}
+
+// bf16 output: c[] <- packed bf16x2 of C. BIAS_GELU also produces u[] = packed bf16(alpha*acc+bias)
+// (the aux output, feed_forward.py:26 pre-activation); DGELU consumes u[].
+//   BIAS_GELU: C = dropout(u * Phi(u))          DGELU: C = alpha*acc * mask/(1-p) * (Phi(u) + u phi(u))
+template <int MODE>
+__device__ __forceinline__ void epilogue_math_bf16(const float (&v)[32], uint32_t (&c)[16], uint32_t (&u)[16],
+                                                   const GemmEpi& e, const GemmShape& s, int row, int nb,
+                                                   int ncols) {
+  float b[32];
+  if constexpr (MODE == VITSSL_EPI_BIAS || MODE == VITSSL_EPI_BIAS_GELU) {
+    if (ncols == 32) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + nb + i));
+        b[i] = t.x; b[i + 1] = t.y; b[i + 2] = t.z; b[i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) b[i] = (i < ncols) ? __ldg(e.bias + nb + i) : 0.0f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = 0.0f;
+  }
+  const f32x2 al = pk2(e.alpha, e.alpha);
+  if constexpr (MODE == VITSSL_EPI_NONE || MODE == VITSSL_EPI_BIAS) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float x0, x1;
+      upk2(ffma2(pk2(v[i], v[i + 1]), al, pk2(b[i], b[i + 1])), x0, x1);
+      c[i >> 1] = pack_bf16(x0, x1);
+    }
+  } else {
+    const bool drop = e.drop_thresh16 != 0;
+    const unsigned long long g8 =
+        (static_cast<unsigned long long>(row) * s.N + nb) >> 3;  // N % 8 == 0 enforced when dropping
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float m[8];
+      if (drop) {
+        dropout_scale8(e.seed, e.offset, g8 + g, e.drop_thresh16, e.drop_scale, m);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = 1.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const int i = 8 * g + j;
+        if constexpr (MODE == VITSSL_EPI_BIAS_GELU) {
+          float x0, x1;
+          upk2(ffma2(pk2(v[i], v[i + 1]), al, pk2(b[i], b[i + 1])), x0, x1);
+          const uint32_t up = pack_bf16(x0, x1);
+          u[i >> 1] = up;
+          const float u0 = bf16_lo(up), u1 = bf16_hi(up);
+          const f32x2 h = fmul2(fmul2(pk2(u0, u1), normal_cdf2(u0, u1)), pk2(m[j], m[j + 1]));
+          float h0, h1;
+          upk2(h, h0, h1);
+          c[i >> 1] = pack_bf16(h0, h1);
+        } else {
+          const uint32_t up = u[i >> 1];
+          const float u0 = bf16_lo(up), u1 = bf16_hi(up);
+          const f32x2 uu = pk2(u0, u1);
+          // phi(u) = exp(-u^2/2) / sqrt(2 pi)
+          float a0, a1;
+          upk2(fmul2(fmul2(uu, uu), pk2(-0.72134752044448170f, -0.72134752044448170f)), a0, a1);
+          const f32x2 pdf = pk2(ex2_approx(a0), ex2_approx(a1));
+          const f32x2 upd = fmul2(fmul2(uu, pk2(0.3989422804014327f, 0.3989422804014327f)), pdf);
+          const f32x2 gp = ffma2(upd, pk2(1.0f, 1.0f), normal_cdf2(u0, u1));  // Phi + u phi
+          const f32x2 dv = fmul2(fmul2(fmul2(pk2(v[i], v[i + 1]), al), gp), pk2(m[j], m[j + 1]));
+          float d0, d1;
+          upk2(dv, d0, d1);
+          c[i >> 1] = pack_bf16(d0, d1);
+        }
+      }
+    }
+  }
+}
+
+// 32 bf16 (16 packed words) of row `lane` -> staging tile with rows of 64 bytes in the TMA
+// SWIZZLE_64B pattern (16-byte chunk index ^= (row >> 1) & 3): a quarter-warp's 8 stores hit 8
+// distinct bank groups.
+__device__ __forceinline__ void stage_row_bf16(uint8_t* tile, int lane, const uint32_t (&c)[16]) {
+  const uint32_t base = smem_u32(tile) + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t a = base + ((j ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(c[4 * j]), "r"(c[4 * j + 1]),
+                 "r"(c[4 * j + 2]), "r"(c[4 * j + 3])
+                 : "memory");
+  }
+}
+// 32 fp32 of row `lane` -> staging tile with rows of 128 bytes in the SWIZZLE_128B pattern
+__device__ __forceinline__ void stage_row_f32(uint8_t* tile, int lane, const float (&v)[32]) {
+  const uint32_t base = smem_u32(tile) + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = base + ((j ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__float_as_uint(v[4 * j])),
+                 "r"(__float_as_uint(v[4 * j + 1])), "r"(__float_as_uint(v[4 * j + 2])),
+                 "r"(__float_as_uint(v[4 * j + 3]))
+                 : "memory");
+  }
+}
+// inverse of stage_row_bf16: read row `lane` of a SWIZZLE_64B tile that TMA loaded
+__device__ __forceinline__ void unstage_row_bf16(const uint8_t* tile, int lane, uint32_t (&u)[16]) {
+  const uint32_t base = smem_u32(tile) + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(u[4 * j]), "=r"(u[4 * j + 1]), "=r"(u[4 * j + 2]), "=r"(u[4 * j + 3])
+                 : "r"(base + ((j ^ sw) << 4))
+                 : "memory");
+  }
+}
+
+// ---- staged epilogue of one warp over its share of the persistent tile loop -------------------
+// The warp owns TMEM lanes [32q, 32q+32) and the 32-column chunks [half*NC/2, (half+1)*NC/2).
+template <int BN, int MODE, bool OUT_F32>
+__device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const CUtensorMap* tmap_aux,
+                                                const GemmShape& s, const GemmEpi& e, uint8_t* stg,
+                                                uint64_t* aux_bar, uint64_t* tfull_bar,
+                                                uint64_t* tempty_bar, uint32_t tmem_base, int q,
+                                                int half, int lane) {
+  static_assert(!(OUT_F32 && (MODE == VITSSL_EPI_BIAS_GELU || MODE == VITSSL_EPI_DGELU)),
+                "GELU epilogues write bf16");
+  constexpr int CHUNKS_PER_WARP = BN / 32 / (EPI_WARPS / 4);
+  const int num_work = s.m_tiles * s.n_tiles * s.splits;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  uint32_t cc = 0;  // chunks processed so far: staging buffer = cc & 1, its barrier parity = (cc >> 1) & 1
+  for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    const int n_blk = w % s.n_tiles;
+    const int m_blk = (w / s.n_tiles) % s.m_tiles;
+    const int m0 = m_blk * BLOCK_M;
+    const int n0 = n_blk * BN + half * CHUNKS_PER_WARP * 32;  // first column of this warp's share
+    const int row0 = m0 + q * 32;
+    const int nvalid = max(0, min(CHUNKS_PER_WARP * 32, s.N - n0));
+    const int nchunks = (nvalid + 31) >> 5;
+    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN +
+                          half * CHUNKS_PER_WARP * 32;
+
+    if constexpr (MODE == VITSSL_EPI_DGELU) {
+      if (lane == 0 && nchunks > 0) {  // pre-activation chunk 0: in flight while the MMAs finish
+        mbar_expect_tx(&aux_bar[cc & 1], 2048);
+        tma_load_2d(stg + (cc & 1) * STG_BUF_BYTES + 2048, tmap_aux, &aux_bar[cc & 1], n0, row0);
+      }
+    }
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
+    __syncwarp();
+    if (nchunks == 0) {
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+
+    uint32_t ra[32], rb[32];
+    if (nchunks > 0) tmem_ld_32x32(tcol, ra);
+
+    auto step = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
+      tmem_ld_wait();  // `cur` has landed
+      __syncwarp();
+      if (c + 1 < nchunks) {
+        tmem_ld_32x32(tcol + (c + 1) * 32, nxt);
+      } else {  // this warp's columns are all in registers: hand the TMEM buffer back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      const int nb = n0 + c * 32;
+      const int ncols = min(32, s.N - nb);
+      uint8_t* buf = stg + (cc & 1) * STG_BUF_BYTES;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cur[i]);
+      if constexpr (OUT_F32) {
+        epilogue_math_f32<MODE>(v, e, nb, ncols);
+        if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer two chunks ago
+        __syncwarp();
+        stage_row_f32(buf, lane, v);
+      } else {
+        uint32_t cp[16], up[16];
+        if constexpr (MODE == VITSSL_EPI_DGELU) {
+          if (lane == 0 && c + 1 < nchunks) {  // next chunk's pre-activations into the other buffer
+            const uint32_t nc = cc + 1;       // (its last readers passed the __syncwarp above)
+            mbar_expect_tx(&aux_bar[nc & 1], 2048);
+            tma_load_2d(stg + (nc & 1) * STG_BUF_BYTES + 2048, tmap_aux, &aux_bar[nc & 1], nb + 32, row0);
+          }
+          mbar_wait(&aux_bar[cc & 1], (cc >> 1) & 1);
+          unstage_row_bf16(buf + 2048, lane, up);
+        }
+        epilogue_math_bf16<MODE>(v, cp, up, e, s, row0 + lane, nb, ncols);
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        stage_row_bf16(buf, lane, cp);
+        if constexpr (MODE == VITSSL_EPI_BIAS_GELU) stage_row_bf16(buf + 2048, lane, up);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmap_c, buf, nb, row0);
+        if constexpr (MODE == VITSSL_EPI_BIAS_GELU) tma_store_2d(tmap_aux, buf + 2048, nb, row0);
+        tma_store_commit();
+      }
+      ++cc;
+    };
+#pragma unroll 1
+    for (int c = 0; c < nchunks; c += 2) {
+      step(ra, rb, c);
+      if (c + 1 < nchunks) step(rb, ra, c + 1);
+    }
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+  if (lane == 0) tma_store_wait_all();
+}
+
+// ---- direct epilogue: registers -> global, per-thread row fragments (split-K red.add, or an
+// output whose pitch TMA cannot address). NONE / BIAS only. -------------------------------------
+template <int BN>
+__device__ __forceinline__ void epilogue_direct(const GemmShape& s, const GemmEpi& e,
+                                                uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                uint32_t tmem_base, int q, int half, int lane) {
+  constexpr int CHUNKS_PER_WARP = BN / 32 / (EPI_WARPS / 4);
+  const int num_work = s.m_tiles * s.n_tiles * s.splits;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    const int n_blk = w % s.n_tiles;
+    const int m_blk = (w / s.n_tiles) % s.m_tiles;
+    const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = half * CHUNKS_PER_WARP; c < (half + 1) * CHUNKS_PER_WARP; ++c) {
+      uint32_t r[32];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
+      tmem_ld_wait();
+      if (c == (half + 1) * CHUNKS_PER_WARP - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      const int nb = n0 + c * 32;
+      if (row >= s.M || nb >= s.N) continue;
+      const int ncols = min(32, s.N - nb);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * e.alpha;
+      if (e.mode == VITSSL_EPI_BIAS) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) v[i] += __ldg(e.bias + nb + i);
+      }
+      if (e.atomic) {
+        float* cp = reinterpret_cast<float*>(e.c) + static_cast<long long>(row) * e.ldc + nb;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) atomicAdd(cp + i, v[i]);
+      } else if (e.out_fp32) {
+        float* cp = reinterpret_cast<float*>(e.c) + static_cast<long long>(row) * e.ldc + nb;
+        if (ncols == 32 && e.vec_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) cp[i] = v[i];
+        }
+      } else {
+        __nv_bfloat16* cp =
+            reinterpret_cast<__nv_bfloat16*>(e.c) + static_cast<long long>(row) * e.ldc + nb;
+        if (ncols == 32 && e.vec_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 pk;
+            pk.x = pack_bf16(v[i], v[i + 1]); pk.y = pack_bf16(v[i + 2], v[i + 3]);
+            pk.z = pack_bf16(v[i + 4], v[i + 5]); pk.w = pack_bf16(v[i + 6], v[i + 7]);
+            *reinterpret_cast<uint4*>(cp + i) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) cp[i] = __float2bfloat16_rn(v[i]);
+        }
+      }
+    }
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
 }
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmShape s,
+                    const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c,
+                    const __grid_constant__ CUtensorMap tmap_aux, const GemmShape s,
                     const GemmEpi e) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
@@ -79,11 +404,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;  // 1024-aligned: stage sizes are multiples of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;  // [EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,14 +418,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (e.tma_out) {
+      tma_prefetch_desc(&tmap_c);
+      if (e.mode == VITSSL_EPI_BIAS_GELU || e.mode == VITSSL_EPI_DGELU) tma_prefetch_desc(&tmap_aux);
+    }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
     }
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -185,135 +517,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else {
     // ------------------------------ epilogue ------------------------------
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int n_blk = w % s.n_tiles;
-      const int m_blk = (w / s.n_tiles) % s.m_tiles;
-      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
-      const int row = m0 + q * 32 + lane;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        if (c == BN / 32 - 1) {  // accumulator drained into registers: hand TMEM back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        const int nb = n0 + c * 32;
-        if (row >= s.M || nb >= s.N) continue;
-        const int ncols = min(32, s.N - nb);
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * e.alpha;
-
-        if (e.mode == VITSSL_EPI_BIAS || e.mode == VITSSL_EPI_BIAS_GELU) {
-          if (ncols == 32) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + nb + i));
-              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-            }
-          } else {
-            _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(e.bias + nb + i);
-          }
-        }
-        uint32_t keep = 0xffffffffu;
-        if (e.drop_thresh16 != 0 &&
-            (e.mode == VITSSL_EPI_BIAS_GELU || e.mode == VITSSL_EPI_DGELU)) {
-          const unsigned long long g8 =
-              (static_cast<unsigned long long>(row) * s.N + nb) >> 3;  // N % 8 == 0 enforced
-          keep = 0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            keep |= dropout_keep8(e.seed, e.offset, g8 + g, e.drop_thresh16) << (8 * g);
-        }
-        if (e.mode == VITSSL_EPI_BIAS_GELU) {
-          // u = bf16(acc + b) is saved for backward; h = dropout(gelu(u))
-          __nv_bfloat16* ap = e.aux + static_cast<long long>(row) * e.ld_aux + nb;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
-          if (ncols == 32 && e.vec_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 pk;
-              pk.x = pack_bf16(v[i], v[i + 1]); pk.y = pack_bf16(v[i + 2], v[i + 3]);
-              pk.z = pack_bf16(v[i + 4], v[i + 5]); pk.w = pack_bf16(v[i + 6], v[i + 7]);
-              *reinterpret_cast<uint4*>(ap + i) = pk;
-            }
-          } else {
-            _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) ap[i] = __float2bfloat16_rn(v[i]);
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float wgt;
-            const float cdf = normal_cdf_fast(v[i], wgt);
-            float h = v[i] * cdf;
-            h = ((keep >> i) & 1u) ? h * e.drop_scale : 0.0f;
-            v[i] = h;
-          }
-        } else if (e.mode == VITSSL_EPI_DGELU) {
-          // dU = dH * dropout_mask/(1-p) * gelu'(u), u read back from the forward's aux
-          const __nv_bfloat16* ap = e.aux + static_cast<long long>(row) * e.ld_aux + nb;
-          float u[32];
-          if (ncols == 32 && e.vec_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(ap + i);
-              u[i] = bf16_lo(pk.x); u[i + 1] = bf16_hi(pk.x);
-              u[i + 2] = bf16_lo(pk.y); u[i + 3] = bf16_hi(pk.y);
-              u[i + 4] = bf16_lo(pk.z); u[i + 5] = bf16_hi(pk.z);
-              u[i + 6] = bf16_lo(pk.w); u[i + 7] = bf16_hi(pk.w);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) u[i] = (i < ncols) ? __bfloat162float(ap[i]) : 0.0f;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float wgt;
-            const float cdf = normal_cdf_fast(u[i], wgt);
-            const float g = fmaf(u[i] * 0.3989422804014327f, wgt, cdf);
-            v[i] = ((keep >> i) & 1u) ? v[i] * g * e.drop_scale : 0.0f;
-          }
-        }
-
-        if (e.atomic) {
-          float* cp = reinterpret_cast<float*>(e.c) + static_cast<long long>(row) * e.ldc + nb;
-          _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) atomicAdd(cp + i, v[i]);
-        } else if (e.out_fp32) {
-          float* cp = reinterpret_cast<float*>(e.c) + static_cast<long long>(row) * e.ldc + nb;
-          if (ncols == 32 && e.vec_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-            _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) cp[i] = v[i];
-          }
-        } else {
-          __nv_bfloat16* cp =
-              reinterpret_cast<__nv_bfloat16*>(e.c) + static_cast<long long>(row) * e.ldc + nb;
-          if (ncols == 32 && e.vec_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 pk;
-              pk.x = pack_bf16(v[i], v[i + 1]); pk.y = pack_bf16(v[i + 2], v[i + 3]);
-              pk.z = pack_bf16(v[i + 4], v[i + 5]); pk.w = pack_bf16(v[i + 6], v[i + 7]);
-              *reinterpret_cast<uint4*>(cp + i) = pk;
-            }
-          } else {
-            _Pragma("unroll") for (int i = 0; i < 32; ++i) if (i < ncols) cp[i] = __float2bfloat16_rn(v[i]);
-          }
-        }
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns it drains
+    uint8_t* stg = staging + (warp - 2) * 2 * STG_BUF_BYTES;
+    uint64_t* abar = aux_bar + (warp - 2) * 2;
+    if (!e.tma_out) {
+      epilogue_direct<BN>(s, e, tfull_bar, tempty_bar, tmem_base, q, half, lane);
+    } else if (e.mode == VITSSL_EPI_BIAS_GELU) {
+      epilogue_staged<BN, VITSSL_EPI_BIAS_GELU, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
+                                                       tempty_bar, tmem_base, q, half, lane);
+    } else if (e.mode == VITSSL_EPI_DGELU) {
+      epilogue_staged<BN, VITSSL_EPI_DGELU, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
+                                                   tempty_bar, tmem_base, q, half, lane);
+    } else if (e.mode == VITSSL_EPI_BIAS) {
+      if (e.out_fp32)
+        epilogue_staged<BN, VITSSL_EPI_BIAS, true>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
+                                                   tempty_bar, tmem_base, q, half, lane);
+      else
+        epilogue_staged<BN, VITSSL_EPI_BIAS, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
+                                                    tempty_bar, tmem_base, q, half, lane);
+    } else {
+      if (e.out_fp32)
+        epilogue_staged<BN, VITSSL_EPI_NONE, true>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
+                                                   tempty_bar, tmem_base, q, half, lane);
+      else
+        epilogue_staged<BN, VITSSL_EPI_NONE, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
+                                                    tempty_bar, tmem_base, q, half, lane);
     }
   }
 
@@ -394,8 +623,8 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A,
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s,
-                   const GemmEpi& e, cudaStream_t stream) {
+int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                   const CUtensorMap& tx, const GemmShape& s, const GemmEpi& e, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
   static bool configured = false;  // per instantiation
@@ -410,18 +639,18 @@ int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape
   }
   const int num_work = s.m_tiles * s.n_tiles * s.splits;
   const int grid = num_work < num_sms() ? num_work : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, s, e);
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tx, s, e);
   return check_launch("gemm_tcgen05");
 }
 
 template <bool A_MN, bool B_MN>
-int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s,
-                const GemmEpi& e, cudaStream_t stream) {
+int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                const CUtensorMap& tx, const GemmShape& s, const GemmEpi& e, cudaStream_t stream) {
   switch (bn) {
-    case 64: return launch_tcgen05<64, A_MN, B_MN>(ta, tb, s, e, stream);
-    case 128: return launch_tcgen05<128, A_MN, B_MN>(ta, tb, s, e, stream);
-    case 192: return launch_tcgen05<192, A_MN, B_MN>(ta, tb, s, e, stream);
-    default: return launch_tcgen05<256, A_MN, B_MN>(ta, tb, s, e, stream);
+    case 64: return launch_tcgen05<64, A_MN, B_MN>(ta, tb, tc, tx, s, e, stream);
+    case 128: return launch_tcgen05<128, A_MN, B_MN>(ta, tb, tc, tx, s, e, stream);
+    case 192: return launch_tcgen05<192, A_MN, B_MN>(ta, tb, tc, tx, s, e, stream);
+    default: return launch_tcgen05<256, A_MN, B_MN>(ta, tb, tc, tx, s, e, stream);
   }
 }
 
@@ -473,9 +702,14 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   const bool tma_ok = (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
                       (reinterpret_cast<uintptr_t>(B) % 16 == 0) && (lda % 8 == 0) &&
                       (ldb % 8 == 0);
-  if (!tma_ok) {
+  const int elt = out_fp32 ? 4 : 2;
+  const bool gelu_mode = epilogue == VITSSL_EPI_BIAS_GELU || epilogue == VITSSL_EPI_DGELU;
+  bool out_ok = (reinterpret_cast<uintptr_t>(C) % 16 == 0) && ((ldc * elt) % 16 == 0);
+  if (gelu_mode)
+    out_ok = out_ok && !out_fp32 && (reinterpret_cast<uintptr_t>(aux) % 16 == 0) && (ld_aux % 8 == 0);
+  if (!tma_ok || (gelu_mode && !out_ok)) {
     VITSSL_REQUIRE(dropout_p == 0.f, VITSSL_ERR_SHAPE, "gemm: dropout unsupported on unaligned path");
-    e.atomic = 0; e.vec_ok = 0;
+    e.atomic = 0; e.vec_ok = 0; e.tma_out = 0;
     dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + 31) / 32));
     gemm_simt_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A),
                                                reinterpret_cast<const __nv_bfloat16*>(B), (int)M,
@@ -505,9 +739,8 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   s.kblocks_per_split = (s.kblocks_total + splits - 1) / splits;
   s.splits = (s.kblocks_total + s.kblocks_per_split - 1) / s.kblocks_per_split;
   e.atomic = s.splits > 1 ? 1 : 0;
-  const int elt = out_fp32 ? 4 : 2;
-  e.vec_ok = (reinterpret_cast<uintptr_t>(C) % 16 == 0) && ((ldc * elt) % 16 == 0);
-  if (aux) e.vec_ok = e.vec_ok && (reinterpret_cast<uintptr_t>(aux) % 16 == 0) && (ld_aux % 8 == 0);
+  e.vec_ok = out_ok ? 1 : 0;
+  e.tma_out = (out_ok && !e.atomic) ? 1 : 0;
   if (e.atomic) {
     cudaError_t err = cudaMemset2DAsync(C, ldc * 4, 0, N * 4, M, stream);
     if (err != cudaSuccess) {
@@ -516,7 +749,9 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
     }
   }
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc, tx;
+  memset(&tc, 0, sizeof(tc));
+  memset(&tx, 0, sizeof(tx));
   int rc;
   if (!a_mn) rc = make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, BLOCK_M);
   else       rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, 64);
@@ -524,9 +759,19 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, bn);
   else       rc = make_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64);
   if (rc) return rc;
+  if (e.tma_out) {
+    // epilogue staging tiles: 32 rows x 32 columns (bf16: 64-byte rows, SWIZZLE_64B; fp32: 128B)
+    rc = make_tmap_2d(&tc, C, elt, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * elt, 32, 32,
+                      out_fp32 ? 128 : 64);
+    if (rc) return rc;
+    if (gelu_mode) {
+      rc = make_tmap_2d(&tx, aux, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ld_aux * 2, 32, 32, 64);
+      if (rc) return rc;
+    }
+  }
 
-  if (!a_mn && !b_mn) return dispatch_bn<false, false>(bn, ta, tb, s, e, stream);
-  if (!a_mn && b_mn) return dispatch_bn<false, true>(bn, ta, tb, s, e, stream);
-  if (a_mn && b_mn) return dispatch_bn<true, true>(bn, ta, tb, s, e, stream);
-  return dispatch_bn<true, false>(bn, ta, tb, s, e, stream);
+  if (!a_mn && !b_mn) return dispatch_bn<false, false>(bn, ta, tb, tc, tx, s, e, stream);
+  if (!a_mn && b_mn) return dispatch_bn<false, true>(bn, ta, tb, tc, tx, s, e, stream);
+  if (a_mn && b_mn) return dispatch_bn<true, true>(bn, ta, tb, tc, tx, s, e, stream);
+  return dispatch_bn<true, false>(bn, ta, tb, tc, tx, s, e, stream);
 }
