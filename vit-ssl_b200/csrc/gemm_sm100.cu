@@ -62,10 +62,14 @@ template <int BN>
 struct GemmCfg {
   static constexpr int kBBytes = BN * BLOCK_K * 2;
   static constexpr int kStageBytes = A_TILE_BYTES + kBBytes;
-  static constexpr int kMaxStages = (SMEM_LIMIT - 1024 /*align*/ - 512 /*barriers*/ - STG_BYTES) / kStageBytes;
-  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  // the ring is deeper when the epilogue needs no staging tiles (split-K / direct epilogue)
+  static constexpr int kAvail = SMEM_LIMIT - 1024 /*align*/ - 1024 /*barriers*/;
+  static constexpr int kStagesStaged = (kAvail - STG_BYTES) / kStageBytes > 8 ? 8 : (kAvail - STG_BYTES) / kStageBytes;
+  static constexpr int kStagesDirect = kAvail / kStageBytes > 8 ? 8 : kAvail / kStageBytes;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + STG_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int smem_bytes(bool staged) {
+    return 2048 + (staged ? kStagesStaged * kStageBytes + STG_BYTES : kStagesDirect * kStageBytes);
+  }
 };
 
 // ---- epilogue math on one 32-column chunk of one accumulator row (all in registers) ----------
@@ -397,17 +401,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_aux, const GemmShape s,
                     const GemmEpi e) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
   constexpr int STAGE_BYTES = Cfg::kStageBytes;
   constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BN, A_MN, B_MN);
+  const int STAGES = e.tma_out ? Cfg::kStagesStaged : Cfg::kStagesDirect;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
+  uint8_t* smem_al = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* staging = smem + STAGES * STAGE_BYTES;  // 1024-aligned: stage sizes are multiples of 1024
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STG_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  // [barriers 1 KB][ring: STAGES x STAGE_BYTES][staging tiles] — everything 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_al);
+  uint8_t* smem = smem_al + 1024;
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* aux_bar = tempty_bar + 2;  // [EPI_WARPS][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * EPI_WARPS);
@@ -630,7 +636,8 @@ int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t err =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::smem_bytes(false) > Cfg::smem_bytes(true) ? Cfg::smem_bytes(false) : Cfg::smem_bytes(true));
     if (err != cudaSuccess) {
       set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
       return VITSSL_ERR_CUDA;
@@ -639,7 +646,7 @@ int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   }
   const int num_work = s.m_tiles * s.n_tiles * s.splits;
   const int grid = num_work < num_sms() ? num_work : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tx, s, e);
+  kern<<<grid, GEMM_THREADS, Cfg::smem_bytes(e.tma_out != 0), stream>>>(ta, tb, tc, tx, s, e);
   return check_launch("gemm_tcgen05");
 }
 
@@ -727,9 +734,9 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   if (split_k != 0 && out_fp32 && epilogue == VITSSL_EPI_NONE) {
     if (split_k > 0) {
       splits = split_k;
-    } else {  // auto: fill the machine, keep >= 4 k-blocks per split
+    } else {  // auto: one wave — tiles * splits <= SM count — and >= 4 k-blocks per split
       const int tiles = s.m_tiles * s.n_tiles;
-      splits = (num_sms() + tiles - 1) / tiles;
+      splits = num_sms() / tiles;
       const int max_splits = s.kblocks_total / 4 > 0 ? s.kblocks_total / 4 : 1;
       if (splits > max_splits) splits = max_splits;
     }
