@@ -292,3 +292,28 @@ def test_no_cpu_fallback():
     m = ViT(**g["cfg"])
     with pytest.raises(VitsslError):
         m(g["x"])  # CPU tensors: must fail loudly, never fall back
+
+
+def test_models_survive_the_reference_compile_wrapper(monkeypatch):
+    """utils/model_builder.py:182-183 returns torch.compile(model): the wrapper must call straight
+    through our eager regions, keep attribute access (`_orig_mod.` state_dict prefix) and give the
+    same numbers as the bare module."""
+    g = load("simmim")
+    m, mod, idx = _simmim(g)
+    from vit_core.ssl.simmim.masking import mask_tables
+    monkeypatch.setattr(mod, "draw_mask", lambda B, N, r, dev, want_indices=True: (idx, *mask_tables(idx, N)))
+    cm = torch.compile(m)
+    assert all(k.startswith("_orig_mod.") for k in cm.state_dict())
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred, targets = cm(g["x"].cuda())
+        loss = torch.nn.L1Loss()(pred, targets)
+    loss.backward()
+    assert pred.dtype == torch.bfloat16 and rel(pred, g["pred"]) <= ACT_TOL
+    assert abs(loss.item() - g["loss"].item()) <= LOSS_TOL * g["loss"].item()
+    assert m.simmim_head.weight.grad is not None
+    gv = load("vit")
+    from vit_core import ViT
+    v = ViT(**gv["cfg"])
+    v.load_state_dict(gv["weights"])
+    v = torch.compile(v.cuda().eval())
+    assert rel(v(gv["x"].cuda()), gv["logits"]) <= ACT_TOL

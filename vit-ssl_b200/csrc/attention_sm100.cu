@@ -110,40 +110,79 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int nchunks = (p.kv_rows + 31) / 32;
     mbar_wait(bar_s, 0);
     tc_fence_after();
+    // pass 1: row maximum. TMEM loads run one chunk ahead of the arithmetic; only the chunk that
+    // straddles Sk is masked (columns past kv_rows hold stale TMEM data).
     float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(lane_addr + c * 32, r);
-      tmem_ld_wait();
+    {
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(lane_addr, ra);
+      auto pass1 = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
+        tmem_ld_wait();
+        if (c + 1 < nchunks) tmem_ld_32x32(lane_addr + (c + 1) * 32, nxt);
+        if (c * 32 + 32 <= p.Sk) {
+          float m0 = __uint_as_float(cur[0]), m1 = __uint_as_float(cur[1]);
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c * 32 + i < p.Sk) mx = fmaxf(mx, __uint_as_float(r[i]));
-    }
-    const float mneg = -mx * sl2;
-    float sum = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(lane_addr + c * 32, r);
-      tmem_ld_wait();
-      uint32_t pk[16];
+          for (int i = 2; i < 32; i += 2) {
+            m0 = fmaxf(m0, __uint_as_float(cur[i]));
+            m1 = fmaxf(m1, __uint_as_float(cur[i + 1]));
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));
+        } else {
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float e0 = (c * 32 + i < p.Sk) ? exp2f(fmaf(__uint_as_float(r[i]), sl2, mneg)) : 0.f;
-        const float e1 =
-            (c * 32 + i + 1 < p.Sk) ? exp2f(fmaf(__uint_as_float(r[i + 1]), sl2, mneg)) : 0.f;
-        sum += e0 + e1;  // fp32 row sum: exact LSE for the backward recomputation
-        pk[i >> 1] = pack_bf16(e0, e1);
-      }
-      // 32 keys = 4 chunks of 16 bytes inside key block (c >> 1), swizzled by (row & 7)
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int j0 = c * 32 + g * 8;
-        if (j0 < p.kv_rows) {
-          const int chunk = (j0 & 63) >> 3;
-          uint8_t* dst = sP + (j0 >> 6) * 16384 + t * 128 + ((chunk ^ (t & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < p.Sk) mx = fmaxf(mx, __uint_as_float(cur[i]));
         }
+      };
+      for (int c = 0; c < nchunks; c += 2) {
+        pass1(ra, rb, c);
+        if (c + 1 < nchunks) pass1(rb, ra, c + 1);
       }
+    }
+    // pass 2: p = 2^(s * scale*log2e - max * scale*log2e), packed FMA + MUFU.EX2, fp32 row sum
+    const float mneg = -mx * sl2;
+    f32x2 sum2 = pk2(0.f, 0.f);
+    {
+      const f32x2 sl2v = pk2(sl2, sl2), mnegv = pk2(mneg, mneg);
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(lane_addr, ra);
+      auto pass2 = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
+        tmem_ld_wait();
+        if (c + 1 < nchunks) tmem_ld_32x32(lane_addr + (c + 1) * 32, nxt);
+        uint32_t pk[16];
+        const bool full = c * 32 + 32 <= p.Sk;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a0, a1;
+          upk2(ffma2(pk2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2v, mnegv), a0, a1);
+          float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+          if (!full) {
+            e0 = (c * 32 + i < p.Sk) ? e0 : 0.f;
+            e1 = (c * 32 + i + 1 < p.Sk) ? e1 : 0.f;
+          }
+          sum2 = fadd2(sum2, pk2(e0, e1));  // fp32 row sum: exact LSE for the backward recomputation
+          pk[i >> 1] = pack_bf16(e0, e1);
+        }
+        // 32 keys = 4 chunks of 16 bytes inside key block (c >> 1), swizzled by (row & 7)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int j0 = c * 32 + g * 8;
+          if (j0 < p.kv_rows) {
+            const int chunk = (j0 & 63) >> 3;
+            uint8_t* dst = sP + (j0 >> 6) * 16384 + t * 128 + ((chunk ^ (t & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
+        }
+      };
+      for (int c = 0; c < nchunks; c += 2) {
+        pass2(ra, rb, c);
+        if (c + 1 < nchunks) pass2(rb, ra, c + 1);
+      }
+    }
+    float sum;
+    {
+      float s0, s1;
+      upk2(sum2, s0, s1);
+      sum = s0 + s1;
     }
     tc_fence_before();
     fence_proxy_async_smem();
@@ -343,25 +382,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(bar_sdp_full, it & 1);
       tc_fence_after();
       if (it > 0) mbar_wait(bar_pds_free, (it - 1) & 1);  // previous P / dS consumed by the MMAs
-      const float dl = i ? delta1 : delta0, nl = i ? nlse1 : nlse0;
+      // invalid query rows recompute p = 2^(-inf) = 0 (their S rows are zero: TMA zero-fills Q)
       const bool rv = i ? qvalid1 : qvalid0;
+      const float dl = i ? delta1 : delta0, nl = rv ? (i ? nlse1 : nlse0) : -INFINITY;
+      const f32x2 sl2v = pk2(sl2, sl2), nlv = pk2(nl, nl), ndlv = pk2(-dl, -dl);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t s[32], dp[32];
-        __syncwarp();
-        tmem_ld_32x32(lane_addr + COL_S + half * 64 + c * 32, s);
-        tmem_ld_32x32(lane_addr + COL_DP + half * 64 + c * 32, dp);
-        tmem_ld_wait();
         const int key0 = j * 128 + half * 64 + c * 32;
         uint32_t pp[16], dd[16];
+        if (key0 < p.Sk) {
+          uint32_t s[32], dp[32];
+          __syncwarp();
+          tmem_ld_32x32(lane_addr + COL_S + half * 64 + c * 32, s);
+          tmem_ld_32x32(lane_addr + COL_DP + half * 64 + c * 32, dp);
+          tmem_ld_wait();
+          const bool full = key0 + 32 <= p.Sk;
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = 0.f, p1 = 0.f;
-          if (rv && key0 + e < p.Sk) p0 = exp2f(fmaf(__uint_as_float(s[e]), sl2, nl));
-          if (rv && key0 + e + 1 < p.Sk) p1 = exp2f(fmaf(__uint_as_float(s[e + 1]), sl2, nl));
-          pp[e >> 1] = pack_bf16(p0, p1);
-          dd[e >> 1] = pack_bf16(p0 * (__uint_as_float(dp[e]) - dl),
-                                 p1 * (__uint_as_float(dp[e + 1]) - dl));
+          for (int e = 0; e < 32; e += 2) {
+            float a0, a1;
+            upk2(ffma2(pk2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), sl2v, nlv), a0, a1);
+            float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+            if (!full) {
+              p0 = (key0 + e < p.Sk) ? p0 : 0.f;
+              p1 = (key0 + e + 1 < p.Sk) ? p1 : 0.f;
+            }
+            pp[e >> 1] = pack_bf16(p0, p1);
+            float d0, d1;  // dS = P * (dP - delta)
+            upk2(fmul2(pk2(p0, p1), fadd2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ndlv)), d0, d1);
+            dd[e >> 1] = pack_bf16(d0, d1);
+          }
+        } else {  // key chunk entirely past Sk
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pp[e] = dd[e] = 0u;
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {

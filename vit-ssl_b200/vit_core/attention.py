@@ -9,8 +9,10 @@ import torch
 from torch import nn
 
 from ._backend import functional as Fb
+from ._backend import eager
 
 
+@eager
 def ScaledDotProductAttention(query, key, value, return_attn: bool = False):
     """softmax(Q K^T / sqrt(d_k)) V on tensors shaped (..., seq, d). Returns (context, probs|None)."""
     return Fb.scaled_dot_product_attention(query, key, value, return_attn)
@@ -31,6 +33,7 @@ class MultiHeadedAttention(nn.Module):
         self.w_value = nn.Linear(d_model, d_model, bias=False)
         self.final_linear = nn.Linear(d_model, d_model, bias=False)
 
+    @eager
     def forward(self, query, key, value, return_attn: bool = False):
         out, probs = Fb.multi_head_attention(self, query, key, value, return_attn)
         return Fb.autocast_out(out), probs

@@ -9,6 +9,7 @@ from torch import nn
 from ._backend import functional as Fb
 from .attention import MultiHeadedAttention
 from .feed_forward import FeedForwardBlock
+from ._backend import eager
 
 
 class EncoderBlock(nn.Module):
@@ -21,5 +22,6 @@ class EncoderBlock(nn.Module):
         self.drop1 = nn.Dropout(dropout)
         self.drop2 = nn.Dropout(dropout)
 
+    @eager
     def forward(self, x, return_attn=False):
         return Fb.encoder_stack([self], x, return_attn)

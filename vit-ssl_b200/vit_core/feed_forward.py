@@ -4,6 +4,7 @@ the first tcgen05 GEMM; its backward fuses gelu' into the dgrad GEMM."""
 from torch import nn
 
 from ._backend import functional as Fb
+from ._backend import eager
 
 
 class FeedForwardBlock(nn.Module):
@@ -13,6 +14,7 @@ class FeedForwardBlock(nn.Module):
         self.linear_out = nn.Linear(d_ff, d_model)
         self.dropout = nn.Dropout(dropout)
 
+    @eager
     def forward(self, x):
         y = Fb.mlp(x, [self.linear_in, self.linear_out], [True, False], dropout_p=self.dropout.p,
                    training=self.training)

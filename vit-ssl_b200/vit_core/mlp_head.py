@@ -3,6 +3,7 @@ import torch
 from torch import nn
 
 from ._backend import functional as Fb
+from ._backend import eager
 
 
 class MLPHead(nn.Module):
@@ -11,6 +12,7 @@ class MLPHead(nn.Module):
         self.norm = nn.LayerNorm(d_model)
         self.linear = nn.Linear(d_model, num_classes)
 
+    @eager
     def forward(self, x):
         h = Fb.layer_norm(x, self.norm)
         out_dtype = torch.bfloat16 if torch.is_autocast_enabled() else torch.float32

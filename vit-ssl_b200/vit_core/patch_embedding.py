@@ -9,6 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ._backend import functional as Fb
+from ._backend import eager
 
 
 def _check_divisible(h, w, p):
@@ -39,6 +40,7 @@ class DynamicPatchEmbedding(nn.Module):
         grid = F.interpolate(grid.permute(0, 3, 1, 2), size=(w, h), mode="bicubic")
         return torch.cat((cls_pos, grid.permute(0, 2, 3, 1).reshape(1, -1, dim)), dim=1)
 
+    @eager
     def forward(self, x):
         _, _, height, width = x.shape
         if height % self.patch_size != 0 or width % self.patch_size != 0:
@@ -62,6 +64,7 @@ class ConvolutionalPatchEmbedding(nn.Module):
             torch.rand(1, (input_shape[1] // patch_size) ** 2 + 1, embedding_dimension)
         )
 
+    @eager
     def forward(self, x):
         return Fb.embed_patches(x, self, self.conv.weight, self.conv.bias, self.cls_token,
                                 self.positional_embedding, self.patch_size)
@@ -79,6 +82,7 @@ class ManualPatchEmbedding(nn.Module):
             torch.rand(1, (input_shape[1] // patch_size) ** 2 + 1, embedding_dimension)
         )
 
+    @eager
     def forward(self, x):
         return Fb.embed_patches(x, self, self.linear.weight, self.linear.bias, self.cls_token,
                                 self.positional_embedding, self.patch_size)

@@ -7,6 +7,7 @@ from torch import nn
 from torch.nn.utils.parametrizations import weight_norm
 
 from .._backend_access import Fb
+from ..._backend import eager
 
 
 class DINOHead(nn.Module):
@@ -20,6 +21,7 @@ class DINOHead(nn.Module):
         # parameter container only: forward never materialises the fp32 normalised weight
         self.fully_connected = weight_norm(nn.Linear(embed_dim, output_dim), name="weight")
 
+    @eager
     def forward(self, x):
         z = Fb.mlp(x, [self.mlp[0], self.mlp[2], self.mlp[4]], [True, True, False])
         wn = self.fully_connected.parametrizations.weight

@@ -8,6 +8,7 @@ student only (teacher is detached, loss.py:22)."""
 from torch import nn
 
 from .._backend_access import Fb
+from ..._backend import eager
 
 
 class DINOLoss(nn.Module):
@@ -16,6 +17,7 @@ class DINOLoss(nn.Module):
         self.teacher_temp = teacher_temp
         self.student_temp = student_temp
 
+    @eager
     def forward(self, teacher_output, student_output, center):
         if teacher_output.dim() != 3 or student_output.dim() != 3:
             raise ValueError(

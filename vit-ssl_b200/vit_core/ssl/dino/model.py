@@ -19,6 +19,7 @@ from .._backend_access import Fb, dp, ops
 from ...encoder_block import EncoderBlock
 from ...patch_embedding import DynamicPatchEmbedding
 from .head import DINOHead
+from ..._backend import eager
 
 
 class ViTBackbone(nn.Module):
@@ -30,6 +31,7 @@ class ViTBackbone(nn.Module):
         )
         self.patch_embedding = DynamicPatchEmbedding(input_shape, embed_dim, patch_size)
 
+    @eager
     def forward(self, x, return_attn=False):
         x = self.patch_embedding(x)
         x, attn_probs = Fb.encoder_stack(self.encoder_blocks, x, return_attn)
@@ -61,6 +63,7 @@ class DINOViT(nn.Module):
         return self.student_head(self.student_backbone(x))
 
     @torch.no_grad()
+    @eager
     def _update_center(self, teacher_output):
         """center <- m * center + (1 - m) * mean over ALL ranks' teacher rows (model.py:91-99)."""
         t = teacher_output.detach()
@@ -77,6 +80,7 @@ class DINOViT(nn.Module):
         self._update_center(out.detach())
         return out
 
+    @eager
     def forward(self, multi_crop_views: List[torch.Tensor], num_global_views: int):
         dp.maybe_attach(self)
         global_crops = torch.cat(multi_crop_views[:num_global_views], dim=0)
@@ -91,6 +95,7 @@ class DINOViT(nn.Module):
         return teacher_output, student_output
 
     @torch.no_grad()
+    @eager
     def momentum_update_teacher(self, teacher_momentum):
         """theta_t <- m theta_t + (1 - m) theta_s over backbone then head parameters, paired by
         registration order (model.py:126-139) — a single multi-tensor kernel."""
@@ -100,6 +105,7 @@ class DINOViT(nn.Module):
         torch.autograd.graph.increment_version(teacher)  # invalidate the bf16 weight shadows
 
     @torch.no_grad()
+    @eager
     def inference_forward(self, x, return_features=False):
         self.eval()
         features = self.teacher_backbone(x)

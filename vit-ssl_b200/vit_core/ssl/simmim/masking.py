@@ -14,6 +14,7 @@ from typing import Tuple
 import torch
 
 from .._backend_access import ops
+from ..._backend import eager
 
 
 def _draw_with_torch(batch_size, num_patches, num_masked, device):
@@ -22,6 +23,7 @@ def _draw_with_torch(batch_size, num_patches, num_masked, device):
     return idx, bool_mask, rows, inv
 
 
+@eager
 def draw_mask(batch_size: int, num_patches: int, mask_ratio: float, device, want_indices: bool = True):
     """-> (indices int64 [B,n_m] in draw order | None, bool_mask [B,N], rows int32 [B*n_m], inv int32 [B*N])."""
     num_masked = int(num_patches * mask_ratio)

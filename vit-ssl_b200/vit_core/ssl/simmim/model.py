@@ -10,6 +10,7 @@ from torch import nn
 from .._backend_access import Fb, ops
 from ...encoder_block import EncoderBlock
 from .masking import draw_mask
+from ..._backend import eager
 
 
 class SimMIMViT(nn.Module):
@@ -43,6 +44,7 @@ class SimMIMViT(nn.Module):
         masked = Fb.gather_rows(tokens, rows, inv)
         return masked, targets, bool_mask
 
+    @eager
     def forward(self, x, return_bool_mask=False):
         masked, targets, bool_mask = self._encode_masked(x)
         pred = Fb.autocast_out(Fb.mlp(masked, [self.simmim_head], [False]))
@@ -50,6 +52,7 @@ class SimMIMViT(nn.Module):
             return pred, targets, bool_mask.unsqueeze(-1)
         return pred, targets
 
+    @eager
     def reconstruction_loss(self, x):
         """Fused objective: mean |pred - target| over the masked patches (what the reference trainer
         computes with nn.L1Loss on forward()'s outputs, simmim_trainer.py:66-67)."""
@@ -58,6 +61,7 @@ class SimMIMViT(nn.Module):
         return Fb.l1_loss(pred, targets)
 
     @torch.no_grad()
+    @eager
     def inference_forward(self, x, return_patch_features=False):
         self.eval()
         tokens = Fb.embed_patches(x, self, self.projection.weight, self.projection.bias, None,

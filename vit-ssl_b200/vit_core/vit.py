@@ -7,6 +7,7 @@ from ._backend import functional as Fb
 from .encoder_block import EncoderBlock
 from .mlp_head import MLPHead
 from .patch_embedding import ConvolutionalPatchEmbedding
+from ._backend import eager
 
 
 class ViT(nn.Module):
@@ -19,6 +20,7 @@ class ViT(nn.Module):
         self.patch_embedding = ConvolutionalPatchEmbedding(input_shape, embed_dim, patch_size)
         self.classification_head = MLPHead(embed_dim, num_classes)
 
+    @eager
     def forward(self, x, return_attn=False):
         x = self.patch_embedding(x)
         x, attn_probs = Fb.encoder_stack(self.encoder_blocks, x, return_attn)
