@@ -31,37 +31,48 @@ struct AttnFwdParams {
   float scale;
 };
 
-constexpr int FWD_THREADS = 160;
-constexpr int FWD_SMEM_V = 65536;            // P aliases [Q | K | +16K]
-constexpr int FWD_SMEM_BAR = 65536 + 32768;  // barriers after V
+constexpr int FWD_THREADS = 192;  // warps 0-3 softmax (TMEM lane quadrant = warp), 4 = TMA, 5 = MMA
+constexpr int FWD_SMEM_Q = 0;               // 16 KB: 128 query rows x 128 B
+constexpr int FWD_SMEM_K = 16384;           // 32 KB: up to 256 key rows
+constexpr int FWD_SMEM_V = 16384 + 32768;   // 32 KB
+constexpr int FWD_SMEM_BAR = 16384 + 65536;
 constexpr int FWD_SMEM_BYTES = FWD_SMEM_BAR + 128 + 1024;
+constexpr uint32_t FWD_COL_O = 128;  // O accumulator columns [128,192): inside S, past the packed P
 
+// Persistent: each CTA (two per SM) loops over (batch, head, 128-query tile) items. Per item
+//   TMA warp : Q,K as soon as the previous item's S MMA retired; V once its PV MMA retired
+//   MMA warp : S = Q K^T (SS) -> [softmax] -> O = P V with P read from TMEM (TS form)
+//   softmax  : row max, p = 2^((s - max) * scale * log2e) with packed FMAs + MUFU.EX2, P written
+//              back over S in TMEM as packed bf16 (tcgen05.st), then O / rowsum -> global.
+// Nothing of the S x S probability matrix ever reaches shared or global memory
+// (attention.py:20-23 materialises it three times).
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;
-  uint8_t* sP = smem;  // written only after the S MMAs have consumed Q and K
+  uint8_t* sQ = smem + FWD_SMEM_Q;
+  uint8_t* sK = smem + FWD_SMEM_K;
   uint8_t* sV = smem + FWD_SMEM_V;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + FWD_SMEM_BAR);
-  uint64_t* bar_qk = bar + 0;
-  uint64_t* bar_v = bar + 1;
-  uint64_t* bar_s = bar + 2;
-  uint64_t* bar_p = bar + 3;
-  uint64_t* bar_o = bar + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 5);
+  uint64_t* bar_qk = bar + 0;      // Q,K landed
+  uint64_t* bar_v = bar + 1;       // V landed
+  uint64_t* bar_s = bar + 2;       // S MMA retired: S readable, Q/K smem reusable
+  uint64_t* bar_p = bar + 3;       // P written to TMEM by all 128 softmax threads
+  uint64_t* bar_o = bar + 4;       // PV MMA retired: O readable, V smem reusable
+  uint64_t* bar_oread = bar + 5;   // O drained: TMEM reusable for the next item's S
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nq = (p.Sq + 127) / 128;
+  const int items = p.B * p.H * nq;
 
   if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
       mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1);
-      mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+      mbar_init(bar_p, 128); mbar_init(bar_o, 1); mbar_init(bar_oread, 128);
       fence_barrier_init();
     }
     __syncwarp();
@@ -74,145 +85,165 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t kv_bytes = static_cast<uint32_t>(p.kv_rows) * 128u;
 
   if (warp == 4) {
+    // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      mbar_expect_tx(bar_qk, 16384u + kv_bytes);
-      tma_load_3d(sQ, &tmap_q, bar_qk, h * 64, q0, b);
-      tma_load_3d(sK, &tmap_k, bar_qk, h * 64, 0, b);
-      mbar_expect_tx(bar_v, kv_bytes);
-      tma_load_3d(sV, &tmap_v, bar_v, h * 64, 0, b);
-
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
+      int it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
+        if (it > 0) mbar_wait(bar_s, (it - 1) & 1);
+        mbar_expect_tx(bar_qk, 16384u + kv_bytes);
+        tma_load_3d(sQ, &tmap_q, bar_qk, h * 64, qt * 128, b);
+        tma_load_3d(sK, &tmap_k, bar_qk, h * 64, 0, b);
+        if (it > 0) mbar_wait(bar_o, (it - 1) & 1);
+        mbar_expect_tx(bar_v, kv_bytes);
+        tma_load_3d(sV, &tmap_v, bar_v, h * 64, 0, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, p.kv_rows, false, false);
-      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16_ss(tmem, umma_desc_sw128(aq + k * 32, 16, 1024),
-                     umma_desc_sw128(ak + k * 32, 16, 1024), idesc_s, k > 0);
-      umma_commit(bar_s);
-
-      mbar_wait(bar_p, 0);
-      mbar_wait(bar_v, 0);
-      tc_fence_after();
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-      const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), av = smem_u32(sV);
       const int ksteps = p.kv_rows / 16;
-      for (int ks = 0; ks < ksteps; ++ks)
-        umma_bf16_ss(tmem, umma_desc_sw128(ap + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                     umma_desc_sw128(av + ks * 2048, 8192, 1024), idesc_o, ks > 0);
-      umma_commit(bar_o);
+      int it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        mbar_wait(bar_qk, it & 1);
+        if (it > 0) mbar_wait(bar_oread, (it - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem, umma_desc_sw128(aq + k * 32, 16, 1024),
+                       umma_desc_sw128(ak + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, it & 1);
+        mbar_wait(bar_v, it & 1);
+        tc_fence_after();
+        for (int ks = 0; ks < ksteps; ++ks)  // P[128, 16 keys] = 8 packed columns per step
+          umma_bf16_ts(tmem + FWD_COL_O, tmem + ks * 8, umma_desc_sw128(av + ks * 2048, 8192, 1024),
+                       idesc_o, ks > 0);
+        umma_commit(bar_o);
+      }
     }
   } else {
-    // softmax + epilogue: thread t owns query row q0 + t == TMEM lane t
+    // ------------------------------ softmax + epilogue ------------------------------
+    // thread t owns query row qt*128 + t == TMEM lane t
     const int t = threadIdx.x;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const float sl2 = p.scale * kLog2e;
+    const f32x2 sl2v = pk2(sl2, sl2);
     const int nchunks = (p.kv_rows + 31) / 32;
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    // pass 1: row maximum. TMEM loads run one chunk ahead of the arithmetic; only the chunk that
-    // straddles Sk is masked (columns past kv_rows hold stale TMEM data).
-    float mx = -INFINITY;
-    {
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32(lane_addr, ra);
-      auto pass1 = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
-        tmem_ld_wait();
-        if (c + 1 < nchunks) tmem_ld_32x32(lane_addr + (c + 1) * 32, nxt);
-        if (c * 32 + 32 <= p.Sk) {
-          float m0 = __uint_as_float(cur[0]), m1 = __uint_as_float(cur[1]);
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
+      mbar_wait(bar_s, it & 1);
+      tc_fence_after();
+      // pass 1: row maximum (TMEM loads run one chunk ahead; only the chunk straddling Sk is masked)
+      float mx = -INFINITY;
+      {
+        uint32_t ra[32], rb[32];
+        __syncwarp();
+        tmem_ld_32x32(lane_addr, ra);
+        auto pass1 = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
+          tmem_ld_wait();
+          if (c + 1 < nchunks) tmem_ld_32x32(lane_addr + (c + 1) * 32, nxt);
+          if (c * 32 + 32 <= p.Sk) {
+            float m0 = __uint_as_float(cur[0]), m1 = __uint_as_float(cur[1]);
 #pragma unroll
-          for (int i = 2; i < 32; i += 2) {
-            m0 = fmaxf(m0, __uint_as_float(cur[i]));
-            m1 = fmaxf(m1, __uint_as_float(cur[i + 1]));
+            for (int i = 2; i < 32; i += 2) {
+              m0 = fmaxf(m0, __uint_as_float(cur[i]));
+              m1 = fmaxf(m1, __uint_as_float(cur[i + 1]));
+            }
+            mx = fmaxf(mx, fmaxf(m0, m1));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < p.Sk) mx = fmaxf(mx, __uint_as_float(cur[i]));
           }
-          mx = fmaxf(mx, fmaxf(m0, m1));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < p.Sk) mx = fmaxf(mx, __uint_as_float(cur[i]));
+        };
+        for (int c = 0; c < nchunks; c += 2) {
+          pass1(ra, rb, c);
+          if (c + 1 < nchunks) pass1(rb, ra, c + 1);
         }
-      };
-      for (int c = 0; c < nchunks; c += 2) {
-        pass1(ra, rb, c);
-        if (c + 1 < nchunks) pass1(rb, ra, c + 1);
       }
-    }
-    // pass 2: p = 2^(s * scale*log2e - max * scale*log2e), packed FMA + MUFU.EX2, fp32 row sum
-    const float mneg = -mx * sl2;
-    f32x2 sum2 = pk2(0.f, 0.f);
-    {
-      const f32x2 sl2v = pk2(sl2, sl2), mnegv = pk2(mneg, mneg);
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32(lane_addr, ra);
-      auto pass2 = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
-        tmem_ld_wait();
-        if (c + 1 < nchunks) tmem_ld_32x32(lane_addr + (c + 1) * 32, nxt);
-        uint32_t pk[16];
-        const bool full = c * 32 + 32 <= p.Sk;
+      // pass 2: P over S in place (chunk c of 32 fp32 columns -> 16 packed bf16x2 columns at 16c)
+      const float mneg = -mx * sl2;
+      const f32x2 mnegv = pk2(mneg, mneg);
+      f32x2 sum2 = pk2(0.f, 0.f);
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(lane_addr, ra);
+        auto pass2 = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
+          tmem_ld_wait();
+          if (c + 1 < nchunks) tmem_ld_32x32(lane_addr + (c + 1) * 32, nxt);
+          uint32_t pk[16];
+          const bool full = c * 32 + 32 <= p.Sk;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a0, a1;
-          upk2(ffma2(pk2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2v, mnegv), a0, a1);
-          float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
-          if (!full) {
-            e0 = (c * 32 + i < p.Sk) ? e0 : 0.f;
-            e1 = (c * 32 + i + 1 < p.Sk) ? e1 : 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1;
+            upk2(ffma2(pk2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2v, mnegv), a0, a1);
+            float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+            if (!full) {
+              e0 = (c * 32 + i < p.Sk) ? e0 : 0.f;
+              e1 = (c * 32 + i + 1 < p.Sk) ? e1 : 0.f;
+            }
+            sum2 = fadd2(sum2, pk2(e0, e1));  // fp32 row sum: exact LSE for the backward recomputation
+            pk[i >> 1] = pack_bf16(e0, e1);
           }
-          sum2 = fadd2(sum2, pk2(e0, e1));  // fp32 row sum: exact LSE for the backward recomputation
-          pk[i >> 1] = pack_bf16(e0, e1);
+          tmem_st_32x16(lane_addr + c * 16, pk);
+        };
+        for (int c = 0; c < nchunks; c += 2) {
+          pass2(ra, rb, c);
+          if (c + 1 < nchunks) pass2(rb, ra, c + 1);
         }
-        // 32 keys = 4 chunks of 16 bytes inside key block (c >> 1), swizzled by (row & 7)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int j0 = c * 32 + g * 8;
-          if (j0 < p.kv_rows) {
-            const int chunk = (j0 & 63) >> 3;
-            uint8_t* dst = sP + (j0 >> 6) * 16384 + t * 128 + ((chunk ^ (t & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          }
-        }
-      };
-      for (int c = 0; c < nchunks; c += 2) {
-        pass2(ra, rb, c);
-        if (c + 1 < nchunks) pass2(rb, ra, c + 1);
       }
-    }
-    float sum;
-    {
-      float s0, s1;
-      upk2(sum2, s0, s1);
-      sum = s0 + s1;
-    }
-    tc_fence_before();
-    fence_proxy_async_smem();
-    mbar_arrive(bar_p);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      float sum;
+      {
+        float s0, s1;
+        upk2(sum2, s0, s1);
+        sum = s0 + s1;
+      }
 
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    const int qrow = q0 + t;
-    const float inv = 1.0f / sum;
+      mbar_wait(bar_o, it & 1);
+      tc_fence_after();
+      const int qrow = qt * 128 + t;
+      const float inv = 1.0f / sum;
+      {
+        uint32_t r0[32], r1[32];
+        __syncwarp();
+        tmem_ld_32x32(lane_addr + FWD_COL_O, r0);
+        tmem_ld_32x32(lane_addr + FWD_COL_O + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_oread);  // O is in registers: the next item's S MMA may overwrite TMEM
+        if (qrow < p.Sq) {
+          __nv_bfloat16* op = p.out + (static_cast<long long>(b) * p.Sq + qrow) * p.ldo + h * 64;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      __syncwarp();
-      tmem_ld_32x32(lane_addr + c * 32, r);
-      tmem_ld_wait();
-      if (qrow < p.Sq) {
-        __nv_bfloat16* op = p.out + (static_cast<long long>(b) * p.Sq + qrow) * p.ldo + h * 64 + c * 32;
+          for (int i = 0; i < 32; i += 8) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r0[i]) * inv, __uint_as_float(r0[i + 1]) * inv);
+            o.y = pack_bf16(__uint_as_float(r0[i + 2]) * inv, __uint_as_float(r0[i + 3]) * inv);
+            o.z = pack_bf16(__uint_as_float(r0[i + 4]) * inv, __uint_as_float(r0[i + 5]) * inv);
+            o.w = pack_bf16(__uint_as_float(r0[i + 6]) * inv, __uint_as_float(r0[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + i) = o;
+          }
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
-          o.y = pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
-          o.z = pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
-          o.w = pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + i) = o;
+          for (int i = 0; i < 32; i += 8) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r1[i]) * inv, __uint_as_float(r1[i + 1]) * inv);
+            o.y = pack_bf16(__uint_as_float(r1[i + 2]) * inv, __uint_as_float(r1[i + 3]) * inv);
+            o.z = pack_bf16(__uint_as_float(r1[i + 4]) * inv, __uint_as_float(r1[i + 5]) * inv);
+            o.w = pack_bf16(__uint_as_float(r1[i + 6]) * inv, __uint_as_float(r1[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + 32 + i) = o;
+          }
+          if (p.lse)
+            p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qrow] = mx * p.scale + __logf(sum);
         }
       }
     }
-    if (qrow < p.Sq && p.lse)
-      p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qrow] = mx * p.scale + __logf(sum);
   }
   tc_fence_before();
   __syncthreads();
@@ -657,7 +688,9 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
     if (err != cudaSuccess) { set_error("attention_fwd: smem attribute: %s", cudaGetErrorString(err)); return VITSSL_ERR_CUDA; }
     configured = true;
   }
-  dim3 grid((unsigned)((Sq + 127) / 128), (unsigned)H, (unsigned)B);
+  const long long items = (long long)B * H * ((Sq + 127) / 128);
+  const long long slots = 2ll * num_sms();  // persistent: two CTAs per SM
+  const unsigned grid = (unsigned)(items < slots ? items : slots);
   attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM_BYTES, stream>>>(mq, mk, mv, p);
   return check_launch("attention_fwd");
 }

@@ -34,7 +34,13 @@ def _prof_end(kind, e0, work):
 
 
 def _p(t):
-    return None if t is None else t.data_ptr()
+    """Device pointer of a tensor argument (None -> NULL). A host tensor never reaches a kernel:
+    there is no CPU fallback, and a host pointer would fault the whole CUDA context."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _l.VitsslError("vitssl_b200 ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
 
 
 def _check_cuda(*ts):
@@ -227,7 +233,7 @@ def attention_generic_bwd(q, k, v, out, d_out, lse, scale):
 # ----------------------------------------------------------------------------------------
 def _ptr_array(tensors):
     import ctypes
-    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return (ctypes.c_void_p * len(tensors))(*[_p(t) for t in tensors])
 
 
 def _numel_array(tensors):
