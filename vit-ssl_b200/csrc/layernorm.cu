@@ -26,79 +26,131 @@ struct LnFwdArgs {
   uint32_t drop_thresh16; float drop_scale; unsigned long long seed, offset;
 };
 
+// 8 consecutive elements of a row as four packed fp32 pairs (FFMA2 / FADD2 / FMUL2 operate on both)
+struct Vec8 {
+  f32x2 p[4];
+};
+__device__ __forceinline__ Vec8 load8_f32(const float* ptr) {
+  const float4 a = *reinterpret_cast<const float4*>(ptr);
+  const float4 b = *reinterpret_cast<const float4*>(ptr + 4);
+  Vec8 v;
+  v.p[0] = pk2(a.x, a.y); v.p[1] = pk2(a.z, a.w); v.p[2] = pk2(b.x, b.y); v.p[3] = pk2(b.z, b.w);
+  return v;
+}
+__device__ __forceinline__ Vec8 ldg8_f32(const float* ptr) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(ptr));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(ptr + 4));
+  Vec8 v;
+  v.p[0] = pk2(a.x, a.y); v.p[1] = pk2(a.z, a.w); v.p[2] = pk2(b.x, b.y); v.p[3] = pk2(b.z, b.w);
+  return v;
+}
+__device__ __forceinline__ void store8_f32(float* ptr, const Vec8& v) {
+  float4 a, b;
+  upk2(v.p[0], a.x, a.y); upk2(v.p[1], a.z, a.w); upk2(v.p[2], b.x, b.y); upk2(v.p[3], b.z, b.w);
+  *reinterpret_cast<float4*>(ptr) = a;
+  *reinterpret_cast<float4*>(ptr + 4) = b;
+}
+__device__ __forceinline__ Vec8 load8_bf16(const __nv_bfloat16* ptr) {
+  const uint4 b = *reinterpret_cast<const uint4*>(ptr);
+  Vec8 v;
+  v.p[0] = pk2(bf16_lo(b.x), bf16_hi(b.x)); v.p[1] = pk2(bf16_lo(b.y), bf16_hi(b.y));
+  v.p[2] = pk2(bf16_lo(b.z), bf16_hi(b.z)); v.p[3] = pk2(bf16_lo(b.w), bf16_hi(b.w));
+  return v;
+}
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* ptr, const Vec8& v) {
+  uint4 pk;
+  float a, b;
+  upk2(v.p[0], a, b); pk.x = pack_bf16(a, b);
+  upk2(v.p[1], a, b); pk.y = pack_bf16(a, b);
+  upk2(v.p[2], a, b); pk.z = pack_bf16(a, b);
+  upk2(v.p[3], a, b); pk.w = pack_bf16(a, b);
+  *reinterpret_cast<uint4*>(ptr) = pk;
+}
+__device__ __forceinline__ float hsum8(const Vec8& v) {
+  float a, b;
+  upk2(fadd2(fadd2(v.p[0], v.p[1]), fadd2(v.p[2], v.p[3])), a, b);
+  return a + b;
+}
+// keep-multipliers (0 or 1/(1-p)) of the 8 elements of dropout group `group8`
+__device__ __forceinline__ Vec8 dropout_mult8(unsigned long long seed, unsigned long long offset,
+                                              unsigned long long group8, uint32_t thresh16, float scale) {
+  float m[8];
+  dropout_scale8(seed, offset, group8, thresh16, scale, m);
+  Vec8 v;
+  v.p[0] = pk2(m[0], m[1]); v.p[1] = pk2(m[2], m[3]); v.p[2] = pk2(m[4], m[5]); v.p[3] = pk2(m[6], m[7]);
+  return v;
+}
+
 template <int NG>  // NG = ceil(D / 256), D % 8 == 0
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnFwdArgs a) {
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
-  if (row >= a.rows) return;
+  const f32x2 zero = pk2(0.f, 0.f);
+  // grid-stride over rows: a few resident CTAs per SM stream the whole tensor
+  for (long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5); row < a.rows;
+       row += static_cast<long long>(gridDim.x) * LN_WARPS) {
   const float* xr = a.x + row * a.ldx;
-  float v[NG][8];
+  Vec8 v[NG];
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     const int c = (g * 32 + lane) * 8;
     if (c < a.D) {
-      const float4 p0 = *reinterpret_cast<const float4*>(xr + c);
-      const float4 p1 = *reinterpret_cast<const float4*>(xr + c + 4);
-      v[g][0] = p0.x; v[g][1] = p0.y; v[g][2] = p0.z; v[g][3] = p0.w;
-      v[g][4] = p1.x; v[g][5] = p1.y; v[g][6] = p1.z; v[g][7] = p1.w;
+      v[g] = load8_f32(xr + c);
       if (a.branch) {
-        const uint4 b = *reinterpret_cast<const uint4*>(a.branch + row * a.D + c);
-        float bf[8] = {bf16_lo(b.x), bf16_hi(b.x), bf16_lo(b.y), bf16_hi(b.y),
-                       bf16_lo(b.z), bf16_hi(b.z), bf16_lo(b.w), bf16_hi(b.w)};
+        const Vec8 bf = load8_bf16(a.branch + row * a.D + c);
         if (a.drop_thresh16) {
-          const uint32_t keep = dropout_keep8(a.seed, a.offset,
-                                              static_cast<unsigned long long>(row * a.D + c) >> 3,
-                                              a.drop_thresh16);
+          const Vec8 m = dropout_mult8(a.seed, a.offset, static_cast<unsigned long long>(row * a.D + c) >> 3,
+                                       a.drop_thresh16, a.drop_scale);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bf[i] = ((keep >> i) & 1u) ? bf[i] * a.drop_scale : 0.f;
+          for (int i = 0; i < 4; ++i) v[g].p[i] = ffma2(bf.p[i], m.p[i], v[g].p[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[g].p[i] = fadd2(v[g].p[i], bf.p[i]);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[g][i] += bf[i];
-        float* xo = a.x_out + row * a.D + c;
-        *reinterpret_cast<float4*>(xo) = make_float4(v[g][0], v[g][1], v[g][2], v[g][3]);
-        *reinterpret_cast<float4*>(xo + 4) = make_float4(v[g][4], v[g][5], v[g][6], v[g][7]);
+        store8_f32(a.x_out + row * a.D + c, v[g]);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
+      for (int i = 0; i < 4; ++i) v[g].p[i] = zero;
     }
   }
-  if (a.gamma == nullptr) return;
+  if (a.gamma == nullptr) continue;
   float s = 0.f;
 #pragma unroll
-  for (int g = 0; g < NG; ++g)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += v[g][i];
+  for (int g = 0; g < NG; ++g) s += hsum8(v[g]);
   const float mean = warp_sum(s) / a.D;
-  float sq = 0.f;
+  const f32x2 nmean = pk2(-mean, -mean);
+  f32x2 sq2 = zero;
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     const int c = (g * 32 + lane) * 8;
     if (c < a.D) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = v[g][i] - mean; sq += d * d; }
+      for (int i = 0; i < 4; ++i) {
+        v[g].p[i] = fadd2(v[g].p[i], nmean);  // centred values, reused by the normalisation
+        sq2 = ffma2(v[g].p[i], v[g].p[i], sq2);
+      }
     }
+  }
+  float sq;
+  {
+    float q0, q1;
+    upk2(sq2, q0, q1);
+    sq = q0 + q1;
   }
   const float rstd = rsqrtf(warp_sum(sq) / a.D + a.eps);
   if (lane == 0) { a.mean[row] = mean; a.rstd[row] = rstd; }
+  const f32x2 rstd2 = pk2(rstd, rstd);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     const int c = (g * 32 + lane) * 8;
     if (c < a.D) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + c + 4));
-      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
+      const Vec8 gm = ldg8_f32(a.gamma + c), bt = ldg8_f32(a.beta + c);
+      Vec8 o;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (v[g][i] - mean) * rstd * gm[i] + bt[i];
-      uint4 pk;
-      pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
-      pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
-      *reinterpret_cast<uint4*>(a.y + row * a.D + c) = pk;
+      for (int i = 0; i < 4; ++i) o.p[i] = ffma2(fmul2(v[g].p[i], rstd2), gm.p[i], bt.p[i]);
+      store8_bf16(a.y + row * a.D + c, o);
     }
+  }
   }
 }
 
@@ -146,82 +198,72 @@ struct LnBwdArgs {
 };
 
 template <int NG>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdArgs a) {
+__global__ void __launch_bounds__(LN_WARPS * 32, NG <= 2 ? 4 : 2) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float red[LN_WARPS][NG * 256 + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float dg[NG][8], db[NG][8];
+  const f32x2 zero = pk2(0.f, 0.f);
+  Vec8 dg[NG], db[NG];
 #pragma unroll
   for (int g = 0; g < NG; ++g)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { dg[g][i] = 0.f; db[g][i] = 0.f; }
+    for (int i = 0; i < 4; ++i) { dg[g].p[i] = zero; db[g].p[i] = zero; }
 
   for (long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp; row < a.rows;
        row += static_cast<long long>(gridDim.x) * LN_WARPS) {
-    float dyv[NG][8], xh[NG][8];
-    float c1 = 0.f, c2 = 0.f;
+    Vec8 dyv[NG], xh[NG], res[NG];
+    f32x2 c1v = zero, c2v = zero;
     float mean = 0.f, rstd = 0.f;
     if (a.dy) { mean = a.mean[row]; rstd = a.rstd[row]; }
+    const f32x2 rstd2 = pk2(rstd, rstd), nmr = pk2(-mean * rstd, -mean * rstd);
+    // every load of the row is issued before the first reduction
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       const int c = (g * 32 + lane) * 8;
-      if (a.dy && c < a.D) {
-        const uint4 p = *reinterpret_cast<const uint4*>(a.dy + row * a.D + c);
-        const float d[8] = {bf16_lo(p.x), bf16_hi(p.x), bf16_lo(p.y), bf16_hi(p.y),
-                            bf16_lo(p.z), bf16_hi(p.z), bf16_lo(p.w), bf16_hi(p.w)};
-        const float4 x0 = *reinterpret_cast<const float4*>(a.x + row * a.ldx + c);
-        const float4 x1 = *reinterpret_cast<const float4*>(a.x + row * a.ldx + c + 4);
-        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c + 4));
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      if (c < a.D) {
+        if (a.dres) res[g] = load8_f32(a.dres + row * a.ld_dres + c);
+        if (a.dy) {
+          const Vec8 d = load8_bf16(a.dy + row * a.D + c);
+          const Vec8 xs = load8_f32(a.x + row * a.ldx + c);
+          const Vec8 gm = ldg8_f32(a.gamma + c);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xh[g][i] = (xs[i] - mean) * rstd;
-          dg[g][i] += d[i] * xh[g][i];
-          db[g][i] += d[i];
-          dyv[g][i] = d[i] * gm[i];
-          c1 += dyv[g][i];
-          c2 += dyv[g][i] * xh[g][i];
+          for (int i = 0; i < 4; ++i) {
+            xh[g].p[i] = ffma2(xs.p[i], rstd2, nmr);          // (x - mean) * rstd
+            dg[g].p[i] = ffma2(d.p[i], xh[g].p[i], dg[g].p[i]);
+            db[g].p[i] = fadd2(db[g].p[i], d.p[i]);
+            dyv[g].p[i] = fmul2(d.p[i], gm.p[i]);
+            c1v = fadd2(c1v, dyv[g].p[i]);
+            c2v = ffma2(dyv[g].p[i], xh[g].p[i], c2v);
+          }
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { dyv[g][i] = 0.f; xh[g][i] = 0.f; }
       }
     }
+    f32x2 ka = zero, kb = zero, kc = zero;  // dx = ka * dyv + kb + kc * xh
     if (a.dy) {
-      c1 = warp_sum(c1) / a.D;
-      c2 = warp_sum(c2) / a.D;
+      float s1a, s1b, s2a, s2b;
+      upk2(c1v, s1a, s1b);
+      upk2(c2v, s2a, s2b);
+      const float c1 = warp_sum(s1a + s1b) / a.D, c2 = warp_sum(s2a + s2b) / a.D;
+      ka = rstd2; kb = pk2(-rstd * c1, -rstd * c1); kc = pk2(-rstd * c2, -rstd * c2);
     }
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       const int c = (g * 32 + lane) * 8;
       if (c < a.D) {
-        float o[8];
+        Vec8 o;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = a.dy ? rstd * (dyv[g][i] - c1 - xh[g][i] * c2) : 0.f;
-        if (a.dres) {
-          const float4 r0 = *reinterpret_cast<const float4*>(a.dres + row * a.ld_dres + c);
-          const float4 r1 = *reinterpret_cast<const float4*>(a.dres + row * a.ld_dres + c + 4);
-          o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
-          o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+        for (int i = 0; i < 4; ++i) {
+          o.p[i] = a.dy ? ffma2(xh[g].p[i], kc, ffma2(dyv[g].p[i], ka, kb)) : zero;
+          if (a.dres) o.p[i] = fadd2(o.p[i], res[g].p[i]);
         }
-        if (a.dx) {
-          float* dxp = a.dx + row * a.ld_dx + c;
-          *reinterpret_cast<float4*>(dxp) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(dxp + 4) = make_float4(o[4], o[5], o[6], o[7]);
-        }
+        if (a.dx) store8_f32(a.dx + row * a.ld_dx + c, o);
         if (a.dbranch) {
           if (a.drop_thresh16) {
-            const uint32_t keep = dropout_keep8(
-                a.seed, a.offset, static_cast<unsigned long long>(row * a.D + c) >> 3,
-                a.drop_thresh16);
+            const Vec8 m = dropout_mult8(a.seed, a.offset, static_cast<unsigned long long>(row * a.D + c) >> 3,
+                                         a.drop_thresh16, a.drop_scale);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * a.drop_scale : 0.f;
+            for (int i = 0; i < 4; ++i) o.p[i] = fmul2(o.p[i], m.p[i]);
           }
-          uint4 pk;
-          pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
-          pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
-          *reinterpret_cast<uint4*>(a.dbranch + row * a.D + c) = pk;
+          store8_bf16(a.dbranch + row * a.D + c, o);
         }
       }
     }
@@ -232,8 +274,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdArgs a
 #pragma unroll
     for (int g = 0; g < NG; ++g)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        red[warp][(g * 32 + lane) * 8 + i] = pass == 0 ? dg[g][i] : db[g][i];
+      for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        upk2(pass == 0 ? dg[g].p[i] : db[g].p[i], lo, hi);
+        red[warp][(g * 32 + lane) * 8 + 2 * i] = lo;
+        red[warp][(g * 32 + lane) * 8 + 2 * i + 1] = hi;
+      }
     __syncthreads();
     for (int c = threadIdx.x; c < a.D; c += LN_WARPS * 32) {
       float s = 0.f;
@@ -309,7 +355,11 @@ extern "C" int vitssl_add_layernorm_fwd(const float* x, int64_t ldx, const void*
   a.mean = mean; a.rstd = rstd; a.rows = rows; a.D = (int)D; a.eps = eps;
   a.drop_thresh16 = static_cast<uint32_t>(dropout_p * 65536.0f);
   a.drop_scale = 1.0f / (1.0f - dropout_p); a.seed = philox_seed; a.offset = philox_offset;
-  const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  const long long want_f = (rows + LN_WARPS - 1) / LN_WARPS;
+  // one warp per row, no grid cap: measured faster than a capped grid-stride launch (44 vs 53 us
+  // for 50176 x 384) — the row loop only matters beyond 2^31 / 4 rows
+  const long long cap_f = (1ll << 31) - 1;
+  const unsigned grid = (unsigned)(want_f < cap_f ? want_f : cap_f);
   const bool fast = (D % 8 == 0) && D <= 1024 && (ldx % 4 == 0) && aligned16(x) &&
                     aligned16(branch) && aligned16(x_out) && aligned16(y) && aligned16(gamma) &&
                     aligned16(beta);
@@ -322,7 +372,7 @@ extern "C" int vitssl_add_layernorm_fwd(const float* x, int64_t ldx, const void*
       default: ln_fwd_kernel<4><<<grid, LN_WARPS * 32, 0, stream>>>(a); break;
     }
   } else {
-    ln_fwd_generic_kernel<<<grid, LN_WARPS * 32, 0, stream>>>(a);
+    ln_fwd_generic_kernel<<<(unsigned)want_f, LN_WARPS * 32, 0, stream>>>(a);
   }
   return check_launch("add_layernorm_fwd");
 }
