@@ -7,6 +7,8 @@
 // per lane per step -> 2x float4 loads of the stream, 1x 16-byte load of the bf16 branch).
 //   fwd traffic / element: 4 (x) + 2 (branch) + 4 (x_out) + 2 (y)            = 12 B
 //   bwd traffic / element: 2 (dy) + 4 (x) + 4 (dres) + 4 (dx) + 2 (dbranch) = 16 B
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "vitssl_b200.h"
 
@@ -402,7 +404,8 @@ extern "C" int vitssl_add_layernorm_bwd(const void* dy, const float* x, int64_t 
   a.drop_thresh16 = static_cast<uint32_t>(dropout_p * 65536.0f);
   a.drop_scale = 1.0f / (1.0f - dropout_p); a.seed = philox_seed; a.offset = philox_offset;
   long long want = (rows + LN_WARPS - 1) / LN_WARPS;
-  const long long cap = static_cast<long long>(num_sms()) * 8;
+  static const int cap_mult = getenv("VITSSL_LN_BWD_CAP") ? atoi(getenv("VITSSL_LN_BWD_CAP")) : 4;  // one resident wave (4 CTAs/SM) measured best
+  const long long cap = static_cast<long long>(num_sms()) * cap_mult;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   const bool fast = (D % 8 == 0) && D <= 1024 && (ldx % 4 == 0) && (ld_dres % 4 == 0) &&
                     (ld_dx % 4 == 0) && aligned16(dy) && aligned16(x) && aligned16(dres) &&
