@@ -81,3 +81,19 @@ def test_dropout_mask_is_shared_between_fwd_and_bwd():
                                           dropout_p=p, seed=5, offset=11)
     assert torch.equal(dbr != 0, keep)
     assert torch.equal(dx, dres)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols", [(50176, 384), (1000, 1536), (777, 768), (513, 1152), (64, 8), (300, 2048),
+                                       (33, 65536), (129, 2304), (5, 16)])
+def test_colsum_bf16_matches_torch(rows, cols):
+    """bias gradients (colsum over rows of a bf16 matrix): dense fast path, wide and strided fallbacks"""
+    from vit_core._backend import ops
+    torch.manual_seed(rows + cols)
+    x = torch.randn(rows, cols, device="cuda").bfloat16()
+    ref = x.double().sum(0)
+    got = ops.colsum_bf16(x)
+    assert got.dtype == torch.float32 and got.shape == (cols,)
+    assert (got.double() - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    xs = torch.randn(rows, cols + 8, device="cuda").bfloat16()[:, :cols]   # row pitch != cols
+    assert (ops.colsum_bf16(xs).double() - xs.double().sum(0)).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())

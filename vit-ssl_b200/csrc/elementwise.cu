@@ -132,6 +132,46 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   }
 }
 
+// dense matrices (ld == cols) whose 16-byte column-group count g = cols / 8 divides the block size:
+// thread t owns column group t % g for the whole kernel and walks the rows t / g, t / g + k, ...
+// with four independent 16-byte loads in flight; one smem reduction + one atomic per column per CTA.
+__global__ void __launch_bounds__(288) colsum_dense_kernel(const __nv_bfloat16* __restrict__ x, long long rows,
+                                                           int g, float* __restrict__ out, int rows_per_cta) {
+  extern __shared__ float red[];  // [blockDim.x][8]
+  const int k = blockDim.x / g;   // rows per pass
+  const int cg = threadIdx.x % g, rl = threadIdx.x / g;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  const uint4* base = reinterpret_cast<const uint4*>(x) + cg;
+  f32x2 acc[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
+  auto add = [&](const uint4& v) {
+    acc[0] = fadd2(acc[0], pk2(bf16_lo(v.x), bf16_hi(v.x)));
+    acc[1] = fadd2(acc[1], pk2(bf16_lo(v.y), bf16_hi(v.y)));
+    acc[2] = fadd2(acc[2], pk2(bf16_lo(v.z), bf16_hi(v.z)));
+    acc[3] = fadd2(acc[3], pk2(bf16_lo(v.w), bf16_hi(v.w)));
+  };
+  long long r = r0 + rl;
+  for (; r + 3ll * k < r1; r += 4ll * k) {
+    const uint4 v0 = __ldg(base + r * g), v1 = __ldg(base + (r + k) * g);
+    const uint4 v2 = __ldg(base + (r + 2ll * k) * g), v3 = __ldg(base + (r + 3ll * k) * g);
+    add(v0); add(v1); add(v2); add(v3);
+  }
+  for (; r < r1; r += k) add(__ldg(base + r * g));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float lo, hi;
+    upk2(acc[i], lo, hi);
+    red[threadIdx.x * 8 + 2 * i] = lo;
+    red[threadIdx.x * 8 + 2 * i + 1] = hi;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < g * 8; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < k; ++j) s += red[(j * g + (c >> 3)) * 8 + (c & 7)];
+    atomicAdd(out + c, s);
+  }
+}
+
 __global__ void colsum_generic_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long rows,
                                       int cols, float* __restrict__ out, int rows_per_cta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,6 +405,21 @@ extern "C" int vitssl_colsum_bf16(const void* x, int64_t ld, int64_t rows, int64
   cudaMemsetAsync(out, 0, cols * sizeof(float), stream);
   if (rows == 0) return 0;
   const bool fast = (cols % 8 == 0) && (ld % 8 == 0) && aligned16(x);
+  if (fast && ld == cols && cols / 8 <= 288) {
+    const int g = (int)(cols / 8);
+    const int threads = (288 / g) * g >= 128 ? (288 / g) * g : g * ((128 + g - 1) / g);
+    if (threads <= 288) {
+      const int k = threads / g;
+      long long ctas = static_cast<long long>(num_sms()) * 4;
+      const long long max_ctas = (rows + 4ll * k - 1) / (4ll * k);
+      if (ctas > max_ctas) ctas = max_ctas;
+      const int rows_per_cta = (int)((((rows + ctas - 1) / ctas) + k - 1) / k * k);
+      const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+      colsum_dense_kernel<<<grid, threads, threads * 8 * sizeof(float), stream>>>(
+          (const __nv_bfloat16*)x, rows, g, out, rows_per_cta);
+      return check_launch("colsum_bf16");
+    }
+  }
   const int col_blocks = (int)((cols + 255) / 256);
   int row_splits = (num_sms() * 4 + col_blocks - 1) / col_blocks;
   if (row_splits > (rows + 31) / 32) row_splits = (int)((rows + 31) / 32);
