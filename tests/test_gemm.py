@@ -141,3 +141,34 @@ def test_gemm_rejects_bad_arguments():
     a, b = _mk((128, 64), 1), _mk((128, 64), 2)
     with pytest.raises(VitsslError):
         ops.gemm(a, b, epilogue=ops.EPI_BIAS)  # bias missing
+
+
+@pytest.mark.parametrize("M,N,K", [(4100, 768, 768), (2048, 1536, 512), (1024, 3072, 768)])
+def test_gemm_cta_pair_mode_epilogues(M, N, K):
+    """N, K >= 512 and M >= 1024 run as CTA pairs (tcgen05 cta_group::2, 256-row tiles): every
+    epilogue, a ragged last tile, MN-major operands and split-K wgrad must match the reference."""
+    ops = _ops()
+    a, w = _mk((M, K), 21), _mk((N, K), 22)
+    bias = torch.randn(N, device="cuda") * 0.1
+    ref = _ref(a, w, False, False)
+    assert _err(ops.gemm(a, w, out_dtype=torch.float32), ref) < 2e-5
+    assert _err(ops.gemm(a, w, epilogue=ops.EPI_BIAS, bias=bias, out_dtype=torch.float32), ref + bias.double()) < 2e-5
+    aux = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    h = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, aux=aux)
+    u_ref = (ref + bias.double()).float().to(torch.bfloat16)
+    assert _err(aux, u_ref.double()) < 8e-3
+    assert _err(h, torch.nn.functional.gelu(aux.double())) < 6e-3
+    dy, w2 = _mk((M, K), 23), _mk((K, N), 24)            # dgrad-shaped: dY[M,K] @ W2[K,N] (b_mn)
+    du = ops.gemm(dy, w2, b_mn=True, epilogue=ops.EPI_DGELU, aux=aux, dropout_p=0.0)
+    u = aux.double()
+    gp = 0.5 * (1 + torch.erf(u / math.sqrt(2))) + u * torch.exp(-0.5 * u * u) / math.sqrt(2 * math.pi)
+    assert _err(du, (dy.double() @ w2.double()) * gp) < 6e-3
+    hd = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, aux=aux, dropout_p=0.25, seed=5, offset=3)
+    dud = ops.gemm(dy, w2, b_mn=True, epilogue=ops.EPI_DGELU, aux=aux, dropout_p=0.25, seed=5, offset=3)
+    live = (h != 0) & (du != 0)
+    assert torch.equal((hd == 0) & live, (dud == 0) & live)   # fwd and bwd regenerate the same mask
+    # wgrad with the token axis as reduction: dW[N, K] = dY^T X, both operands MN-major, split-K
+    g, x = _mk((M, N), 25), _mk((M, K), 26)
+    for split in (0, -1, 3):
+        dw = ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=split)
+        assert _err(dw, g.double().t() @ x.double()) < 2e-5, split

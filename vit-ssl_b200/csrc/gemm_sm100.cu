@@ -17,6 +17,7 @@
 // The dGELU epilogue's pre-activation tile arrives the same way in reverse (TMA load, one chunk
 // ahead). Tiles whose output cannot be a TMA target (row pitch not a multiple of 16 bytes) and
 // split-K partial sums use the direct register->global epilogue.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -58,9 +59,14 @@ struct GemmEpi {
   unsigned long long seed, offset;
 };
 
-template <int BN>
+// PAIR = true: two CTAs of a cluster share one 256 x BN tile (tcgen05 cta_group::2): each CTA
+// stages its own 128 rows of A but only BN/2 columns of B, so the shared-memory fill and the
+// tensor core's operand reads both drop by a third per FLOP — the single-CTA form is bound by
+// shared-memory bandwidth (TMA writes + MMA operand reads) well below the tensor peak.
+template <int BN, bool PAIR>
 struct GemmCfg {
-  static constexpr int kBBytes = BN * BLOCK_K * 2;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;  // B columns staged by this CTA
+  static constexpr int kBBytes = kBRows * BLOCK_K * 2;
   static constexpr int kStageBytes = A_TILE_BYTES + kBBytes;
   // the ring is deeper when the epilogue needs no staging tiles (split-K / direct epilogue)
   static constexpr int kAvail = SMEM_LIMIT - 1024 /*align*/ - 1024 /*barriers*/;
@@ -71,6 +77,17 @@ struct GemmCfg {
     return 2048 + (staged ? kStagesStaged * kStageBytes + STG_BYTES : kStagesDirect * kStageBytes);
   }
 };
+
+// where this CTA sits in the persistent tile loop
+struct TileCtx {
+  int worker, nworkers;   // tile-loop start and stride (CTAs, or CTA pairs)
+  int tile_rows;          // rows of one scheduled tile: 128, or 256 for a pair
+  int row_off;            // this CTA's first row inside the tile (rank * 128)
+  uint32_t tempty_addr;   // shared::cluster address of tempty_bar[0] in the CTA that issues the MMAs
+};
+__device__ __forceinline__ void tempty_arrive(const TileCtx& t, int acc) {
+  mbar_arrive_cluster(t.tempty_addr + acc * 8);
+}
 
 // ---- epilogue math on one 32-column chunk of one accumulator row (all in registers) ----------
 // fp32 output (NONE / BIAS): v[] <- alpha * acc (+ bias)
@@ -220,7 +237,7 @@ template <int BN, int MODE, bool OUT_F32>
 __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const CUtensorMap* tmap_aux,
                                                 const GemmShape& s, const GemmEpi& e, uint8_t* stg,
                                                 uint64_t* aux_bar, uint64_t* tfull_bar,
-                                                uint64_t* tempty_bar, uint32_t tmem_base, int q,
+                                                const TileCtx& tc, uint32_t tmem_base, int q,
                                                 int half, int lane) {
   static_assert(!(OUT_F32 && (MODE == VITSSL_EPI_BIAS_GELU || MODE == VITSSL_EPI_DGELU)),
                 "GELU epilogues write bf16");
@@ -229,10 +246,10 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
   int acc = 0;
   uint32_t acc_phase = 0;
   uint32_t cc = 0;  // chunks processed so far: staging buffer = cc & 1, its barrier parity = (cc >> 1) & 1
-  for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+  for (int w = tc.worker; w < num_work; w += tc.nworkers) {
     const int n_blk = w % s.n_tiles;
     const int m_blk = (w / s.n_tiles) % s.m_tiles;
-    const int m0 = m_blk * BLOCK_M;
+    const int m0 = m_blk * tc.tile_rows + tc.row_off;
     const int n0 = n_blk * BN + half * CHUNKS_PER_WARP * 32;  // first column of this warp's share
     const int row0 = m0 + q * 32;
     const int nvalid = max(0, min(CHUNKS_PER_WARP * 32, s.N - n0));
@@ -251,7 +268,7 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
     __syncwarp();
     if (nchunks == 0) {
       tc_fence_before();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) tempty_arrive(tc, acc);
     }
 
     uint32_t ra[32], rb[32];
@@ -265,7 +282,7 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
       } else {  // this warp's columns are all in registers: hand the TMEM buffer back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) tempty_arrive(tc, acc);
       }
       const int nb = n0 + c * 32;
       const int ncols = min(32, s.N - nb);
@@ -319,16 +336,16 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
 // output whose pitch TMA cannot address). NONE / BIAS only. -------------------------------------
 template <int BN>
 __device__ __forceinline__ void epilogue_direct(const GemmShape& s, const GemmEpi& e,
-                                                uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                uint64_t* tfull_bar, const TileCtx& tc,
                                                 uint32_t tmem_base, int q, int half, int lane) {
   constexpr int CHUNKS_PER_WARP = BN / 32 / (EPI_WARPS / 4);
   const int num_work = s.m_tiles * s.n_tiles * s.splits;
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+  for (int w = tc.worker; w < num_work; w += tc.nworkers) {
     const int n_blk = w % s.n_tiles;
     const int m_blk = (w / s.n_tiles) % s.m_tiles;
-    const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
+    const int m0 = m_blk * tc.tile_rows + tc.row_off, n0 = n_blk * BN;
     const int row = m0 + q * 32 + lane;
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
@@ -341,7 +358,7 @@ __device__ __forceinline__ void epilogue_direct(const GemmShape& s, const GemmEp
       if (c == (half + 1) * CHUNKS_PER_WARP - 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) tempty_arrive(tc, acc);
       }
       const int nb = n0 + c * 32;
       if (row >= s.M || nb >= s.N) continue;
@@ -393,16 +410,17 @@ __device__ __forceinline__ void epilogue_direct(const GemmShape& s, const GemmEp
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c,
                     const __grid_constant__ CUtensorMap tmap_aux, const GemmShape s,
                     const GemmEpi e) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGE_BYTES = Cfg::kStageBytes;
-  constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BN, A_MN, B_MN);
+  constexpr int B_ROWS = Cfg::kBRows;
+  constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 256 : BLOCK_M, BN, A_MN, B_MN);
   const int STAGES = e.tma_out ? Cfg::kStagesStaged : Cfg::kStagesDirect;
 
   extern __shared__ uint8_t smem_raw[];
@@ -420,6 +438,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // rank 0 of a pair issues the MMAs
+  TileCtx tc;
+  tc.worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  tc.nworkers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  tc.tile_rows = PAIR ? 256 : BLOCK_M;
+  tc.row_off = PAIR ? static_cast<int>(rank) * BLOCK_M : 0;
+  tc.tempty_addr = PAIR ? mapa_u32(smem_u32(tempty_bar), 0) : smem_u32(tempty_bar);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -434,14 +459,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI_WARPS);
+      mbar_init(&tempty_bar[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
     for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -452,32 +481,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const uint32_t full0 = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0u;  // the leader's full barriers
+      for (int w = tc.worker; w < num_work; w += tc.nworkers) {
         const int n_blk = w % s.n_tiles;
         const int m_blk = (w / s.n_tiles) % s.m_tiles;
         const int sp = w / (s.n_tiles * s.m_tiles);
         const int kb0 = sp * s.kblocks_per_split;
         const int kb1 = min(kb0 + s.kblocks_per_split, s.kblocks_total);
-        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
+        const int m0 = m_blk * tc.tile_rows + tc.row_off;
+        const int n0 = n_blk * BN + (PAIR ? static_cast<int>(rank) * B_ROWS : 0);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* a_dst = smem + stage * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_TILE_BYTES;
           const int k0 = kb * BLOCK_K;
-          if constexpr (!A_MN) {
-            tma_load_2d(a_dst, &tmap_a, &full_bar[stage], k0, m0);
-          } else {
+          if constexpr (PAIR) {
+            // both CTAs' bytes land on the leader's barrier; only the leader arms it
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            const uint32_t fb = full0 + stage * 8;
+            if constexpr (!A_MN) {
+              tma_load_2d_pair(a_dst, &tmap_a, fb, k0, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_2d(a_dst + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
-          }
-          if constexpr (!B_MN) {
-            tma_load_2d(b_dst, &tmap_b, &full_bar[stage], k0, n0);
-          } else {
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_2d_pair(a_dst + j * 8192, &tmap_a, fb, m0 + 64 * j, k0);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_pair(b_dst, &tmap_b, fb, k0, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(b_dst + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+              for (int j = 0; j < B_ROWS / 64; ++j)
+                tma_load_2d_pair(b_dst + j * 8192, &tmap_b, fb, n0 + 64 * j, k0);
+            }
+          } else {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_2d(a_dst, &tmap_a, &full_bar[stage], k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_2d(a_dst + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(b_dst, &tmap_b, &full_bar[stage], k0, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < B_ROWS / 64; ++j)
+                tma_load_2d(b_dst + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -485,12 +536,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = tc.worker; w < num_work; w += tc.nworkers) {
         const int sp = w / (s.n_tiles * s.m_tiles);
         const int kb0 = sp * s.kblocks_per_split;
         const int kb1 = min(kb0 + s.kblocks_per_split, s.kblocks_total);
@@ -511,12 +562,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                      : umma_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(b_base + k * 2048, 8192, 1024)
                                      : umma_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_bf16_ss(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_bf16_ss_pair(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -528,35 +584,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint8_t* stg = staging + (warp - 2) * 2 * STG_BUF_BYTES;
     uint64_t* abar = aux_bar + (warp - 2) * 2;
     if (!e.tma_out) {
-      epilogue_direct<BN>(s, e, tfull_bar, tempty_bar, tmem_base, q, half, lane);
+      epilogue_direct<BN>(s, e, tfull_bar, tc, tmem_base, q, half, lane);
     } else if (e.mode == VITSSL_EPI_BIAS_GELU) {
       epilogue_staged<BN, VITSSL_EPI_BIAS_GELU, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                       tempty_bar, tmem_base, q, half, lane);
+                                                       tc, tmem_base, q, half, lane);
     } else if (e.mode == VITSSL_EPI_DGELU) {
       epilogue_staged<BN, VITSSL_EPI_DGELU, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                   tempty_bar, tmem_base, q, half, lane);
+                                                   tc, tmem_base, q, half, lane);
     } else if (e.mode == VITSSL_EPI_BIAS) {
       if (e.out_fp32)
         epilogue_staged<BN, VITSSL_EPI_BIAS, true>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                   tempty_bar, tmem_base, q, half, lane);
+                                                   tc, tmem_base, q, half, lane);
       else
         epilogue_staged<BN, VITSSL_EPI_BIAS, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                    tempty_bar, tmem_base, q, half, lane);
+                                                    tc, tmem_base, q, half, lane);
     } else {
       if (e.out_fp32)
         epilogue_staged<BN, VITSSL_EPI_NONE, true>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                   tempty_bar, tmem_base, q, half, lane);
+                                                   tc, tmem_base, q, half, lane);
       else
         epilogue_staged<BN, VITSSL_EPI_NONE, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                    tempty_bar, tmem_base, q, half, lane);
+                                                    tc, tmem_base, q, half, lane);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // no CTA leaves while its peer may still signal it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -628,11 +686,11 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A,
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
 int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                    const CUtensorMap& tx, const GemmShape& s, const GemmEpi& e, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, PAIR>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t err =
@@ -645,19 +703,46 @@ int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     configured = true;
   }
   const int num_work = s.m_tiles * s.n_tiles * s.splits;
-  const int grid = num_work < num_sms() ? num_work : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::smem_bytes(e.tma_out != 0), stream>>>(ta, tb, tc, tx, s, e);
-  return check_launch("gemm_tcgen05");
+  if constexpr (PAIR) {
+    const int pairs = num_sms() / 2;
+    const int nclusters = num_work < pairs ? num_work : pairs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * nclusters);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::smem_bytes(e.tma_out != 0);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tx, s, e);
+    if (err != cudaSuccess) {
+      set_error("gemm: cluster launch failed: %s", cudaGetErrorString(err));
+      return VITSSL_ERR_CUDA;
+    }
+    return check_launch("gemm_tcgen05_pair");
+  } else {
+    const int grid = num_work < num_sms() ? num_work : num_sms();
+    kern<<<grid, GEMM_THREADS, Cfg::smem_bytes(e.tma_out != 0), stream>>>(ta, tb, tc, tx, s, e);
+    return check_launch("gemm_tcgen05");
+  }
 }
 
 template <bool A_MN, bool B_MN>
-int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+int dispatch_bn(int bn, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                 const CUtensorMap& tx, const GemmShape& s, const GemmEpi& e, cudaStream_t stream) {
+  if (pair) {
+    switch (bn) {
+      case 128: return launch_tcgen05<128, A_MN, B_MN, true>(ta, tb, tc, tx, s, e, stream);
+      case 192: return launch_tcgen05<192, A_MN, B_MN, true>(ta, tb, tc, tx, s, e, stream);
+      default: return launch_tcgen05<256, A_MN, B_MN, true>(ta, tb, tc, tx, s, e, stream);
+    }
+  }
   switch (bn) {
-    case 64: return launch_tcgen05<64, A_MN, B_MN>(ta, tb, tc, tx, s, e, stream);
-    case 128: return launch_tcgen05<128, A_MN, B_MN>(ta, tb, tc, tx, s, e, stream);
-    case 192: return launch_tcgen05<192, A_MN, B_MN>(ta, tb, tc, tx, s, e, stream);
-    default: return launch_tcgen05<256, A_MN, B_MN>(ta, tb, tc, tx, s, e, stream);
+    case 64: return launch_tcgen05<64, A_MN, B_MN, false>(ta, tb, tc, tx, s, e, stream);
+    case 128: return launch_tcgen05<128, A_MN, B_MN, false>(ta, tb, tc, tx, s, e, stream);
+    case 192: return launch_tcgen05<192, A_MN, B_MN, false>(ta, tb, tc, tx, s, e, stream);
+    default: return launch_tcgen05<256, A_MN, B_MN, false>(ta, tb, tc, tx, s, e, stream);
   }
 }
 
@@ -724,10 +809,23 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
     return check_launch("gemm_simt");
   }
 
-  const int bn = pick_block_n((int)N);
+  int bn = pick_block_n((int)N);
+  // CTA pairs (cta_group::2) for the compute-bound GEMMs: 256-row tiles, B columns split across
+  // the pair. Measured on B200: +12..19 % where both N and K are large (8192^3: 1162 -> 1388 TF/s,
+  // ViT-B shapes 1240-1360 TF/s = cuBLAS parity); no gain on ViT-S shapes (N or K = 384), which are
+  // bound by HBM and the epilogue, so those stay single-CTA. VITSSL_GEMM_PAIR=0/1/2 = off/auto/force.
+  // An MN-major B operand is staged in 64-column boxes, so its per-CTA half must be a multiple of 64.
+  static const int pair_env = getenv("VITSSL_GEMM_PAIR") ? atoi(getenv("VITSSL_GEMM_PAIR")) : 1;
+  bool pair = pair_env != 0 && M >= 1024 && (M % 256 == 0 || M >= 4096) && N >= 128 &&
+              (pair_env == 2 || (N >= 512 && K >= 512));
+  if (pair) {
+    if (bn == 64) pair = false;
+    if (b_mn && bn == 192) bn = 128;
+  }
+  const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
   GemmShape s{};
   s.M = (int)M; s.N = (int)N; s.K = (int)K;
-  s.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  s.m_tiles = (int)((M + tile_m - 1) / tile_m);
   s.n_tiles = (int)((N + bn - 1) / bn);
   s.kblocks_total = (int)((K + BLOCK_K - 1) / BLOCK_K);
   int splits = 1;
@@ -736,7 +834,7 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
       splits = split_k;
     } else {  // auto: one wave — tiles * splits <= SM count — and >= 4 k-blocks per split
       const int tiles = s.m_tiles * s.n_tiles;
-      splits = num_sms() / tiles;
+      splits = (pair ? num_sms() / 2 : num_sms()) / tiles;
       const int max_splits = s.kblocks_total / 4 > 0 ? s.kblocks_total / 4 : 1;
       if (splits > max_splits) splits = max_splits;
     }
@@ -763,7 +861,7 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   if (!a_mn) rc = make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, BLOCK_M);
   else       rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, 64);
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, bn);
+  if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, pair ? bn / 2 : bn);
   else       rc = make_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64);
   if (rc) return rc;
   if (e.tma_out) {
@@ -777,8 +875,8 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
     }
   }
 
-  if (!a_mn && !b_mn) return dispatch_bn<false, false>(bn, ta, tb, tc, tx, s, e, stream);
-  if (!a_mn && b_mn) return dispatch_bn<false, true>(bn, ta, tb, tc, tx, s, e, stream);
-  if (a_mn && b_mn) return dispatch_bn<true, true>(bn, ta, tb, tc, tx, s, e, stream);
-  return dispatch_bn<true, false>(bn, ta, tb, tc, tx, s, e, stream);
+  if (!a_mn && !b_mn) return dispatch_bn<false, false>(bn, pair, ta, tb, tc, tx, s, e, stream);
+  if (!a_mn && b_mn) return dispatch_bn<false, true>(bn, pair, ta, tb, tc, tx, s, e, stream);
+  if (a_mn && b_mn) return dispatch_bn<true, true>(bn, pair, ta, tb, tc, tx, s, e, stream);
+  return dispatch_bn<true, false>(bn, pair, ta, tb, tc, tx, s, e, stream);
 }
