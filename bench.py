@@ -175,7 +175,9 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=180))
     lib.ensure_device()
     dev = torch.device("cuda", local)
     B = args.batch
@@ -268,12 +270,13 @@ def run_gpu_arm(args):
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
     # ---- instrumented pass: per-kernel-family CUDA-event timing of the same step ----
+    # (every rank runs the step — its gradient all-reduce is collective — rank 0 keeps the events)
     roof = roof_hbm = None
+    ops.PROFILE = []
+    step(dev_in[0])
+    barrier()
+    recs, ops.PROFILE = ops.PROFILE, None
     if rank == 0:
-        ops.PROFILE = []
-        step(dev_in[0])
-        torch.cuda.synchronize()
-        recs, ops.PROFILE = ops.PROFILE, None
         pk = peaks()
         gemm = [(a.elapsed_time(b), w) for (k, a, b, w) in recs if k.startswith("gemm")]
         ln = [(a.elapsed_time(b), w) for (k, a, b, w) in recs if k == "add_layernorm"]
