@@ -116,6 +116,8 @@ def run_reference_arm(args):
 # clocks sampler
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi sampled every 50 ms in the background; `window(t0, t1)` summarises the rows whose
+    host timestamps fall inside a timed region (started well before it: nvidia-smi needs ~0.5 s)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -126,7 +128,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -134,14 +136,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def window(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < t0 or ts > t1 + 0.05:
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -216,15 +223,16 @@ def run_gpu_arm(args):
             return float(t.item())
         return ms
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(dev_in[i % n_host])
     barrier()
 
     # ---- timed region 1: device-resident inputs (B*3*224*224*4 B * 3 buffers = 462 MB > L2) ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     lib.launch_count(reset=True)
+    t_host0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -234,7 +242,7 @@ def run_gpu_arm(args):
     barrier()
     launches = lib.launch_count()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
+    t_host1 = time.time()
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
     final_loss = float(loss.detach())
@@ -268,6 +276,14 @@ def run_gpu_arm(args):
     barrier()
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    clocks = None
+    if rank == 0:
+        # clocks under load: samples inside timed region 1 (and the e2e region right after it when
+        # region 1 is shorter than a few sampling periods)
+        clocks = sampler.window(t_host0, t_host1)
+        if (clocks.get("samples") or 0) < 3:
+            clocks = sampler.window(t_host0, time.time())
+        sampler.stop()
 
     # ---- instrumented pass: per-kernel-family CUDA-event timing of the same step ----
     # (every rank runs the step — its gradient all-reduce is collective — rank 0 keeps the events)

@@ -106,6 +106,47 @@ int vitssl_attention_generic_bwd(const void* q, const void* k, const void* v,
                                  int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t d,
                                  float scale, vitssl_stream_t stream);
 
+/* ---- whole encoder stack in one call (host-side launch sequencing) ---------------------------
+ * The hot loop `for block in encoder_blocks` (vit.py:35-37, ssl/simmim/model.py:52-55,
+ * ssl/dino/model.py:36-38) over EncoderBlock.forward (encoder_block.py:40-52): every kernel of all
+ * L pre-LN blocks is enqueued from C++, forward or backward, with buffers supplied by the caller.
+ * Arrays named `const T* const*` are HOST arrays of L DEVICE pointers. d_head must be 64, S <= 256.
+ * Layer l reads the stream from x_in (l = 0) or xs[l]; xs[0] is unused. Saved-for-backward
+ * buffers: xs, mean1/rstd1, xn1, qkv ([M,3D]), ctx, lse, xmid, mean2/rstd2, xn2, u, h. In
+ * inference every layer may point at the same buffers. */
+typedef struct {
+  int64_t B, S, D, H, F, L;
+  float dropout_p, eps;
+  uint64_t seed;
+  const float* x_in;              /* fp32 [B*S, D] */
+  float* out;                     /* fp32 [B*S, D] */
+  void* y1;                       /* bf16 [B*S, D] scratch */
+  void* y2[2];                    /* bf16 [B*S, D] scratch (ping-pong) */
+  const void* const* wqkv;        /* bf16 [3D, D]: rows = (w_query; w_key; w_value) */
+  const void* const* wo;          /* bf16 [D, D] */
+  const void* const* w1;          /* bf16 [F, D] */
+  const void* const* w2;          /* bf16 [D, F] */
+  const float* const* b1; const float* const* b2;
+  const float* const* g1; const float* const* be1; const float* const* g2; const float* const* be2;
+  float* const* xs; float* const* mean1; float* const* rstd1; void* const* xn1;
+  void* const* qkv; void* const* ctx; float* const* lse;
+  float* const* xmid; float* const* mean2; float* const* rstd2; void* const* xn2;
+  void* const* u; void* const* h;
+} vitssl_encoder_fwd_args;
+int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* args, vitssl_stream_t stream);
+
+typedef struct {
+  const vitssl_encoder_fwd_args* fwd;  /* the forward call's arguments (saved buffers, weights) */
+  const float* gout;                   /* fp32 [B*S, D] gradient of `out` */
+  float* dx;                           /* fp32 [B*S, D] gradient of x_in */
+  void* dbranch; void* du; void* dxn; void* dctx; void* dqkv;  /* bf16 scratch: [M,D] [M,F] [M,D] [M,D] [M,3D] */
+  float* gs[2];                        /* fp32 [B*S, D] scratch (stream gradient ping-pong) */
+  float* const* dwqkv; float* const* dwo; float* const* dw1; float* const* db1;
+  float* const* dw2; float* const* db2;
+  float* const* dg1; float* const* dbe1; float* const* dg2; float* const* dbe2;
+} vitssl_encoder_bwd_args;
+int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* args, vitssl_stream_t stream);
+
 /* ---- weight casts, EMA, bias gradients (host_* arguments are HOST arrays of device pointers) */
 /* fp32 -> bf16 for `count` tensors in one or a few launches (parameters stay fp32 nn.Parameters;
  * the GEMMs read bf16 shadows, like autocast's per-call weight casts). */

@@ -138,6 +138,22 @@ class _EncoderStackFn(torch.autograd.Function):
         p = meta.p if meta.training else 0.0
         seed = _new_seed() if p > 0 else 0
         x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+        if ops.encoder_stack_supported(S, D, H):
+            # one C call enqueues every kernel of the L blocks (csrc/encoder.cu)
+            out, st = ops.encoder_stack_fwd(x, meta.weights, params, H, p, seed, need_grad)
+            probs = None
+            if meta.return_attn:
+                q3 = ops.encoder_stack_last_qkv(st)
+                probs = attention_probs(q3[..., :D], q3[..., D:2 * D], H)
+            if need_grad:
+                ctx.stack_state = st
+                ctx.meta, ctx.params = meta, params
+                ctx.shape = (B, S, D)
+            if probs is not None:
+                ctx.mark_non_differentiable(probs)
+                return out, probs
+            return out
+        ctx.stack_state = None
         stream = x.view(M, D)
         branch = None
         saved = []
@@ -182,12 +198,26 @@ class _EncoderStackFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout, *_):
+        g = gout if (gout.dtype == torch.float32 and gout.is_contiguous()) else gout.float().contiguous()
+        if ctx.stack_state is not None:
+            st, ctx.stack_state = ctx.stack_state, None
+            L = ctx.meta.L
+            D = ctx.shape[2]
+            dx, gr = ops.encoder_stack_bwd(st, g)
+            grads = []
+            for l in range(L):
+                wq = gr["dwqkv"][l]
+                grads += [wq[:D], wq[D:2 * D], wq[2 * D:], gr["dwo"][l], gr["dw1"][l], gr["db1"][l], gr["dw2"][l],
+                          gr["db2"][l], gr["dg1"][l], gr["dbe1"][l], gr["dg2"][l], gr["dbe2"][l]]
+            for i, need in enumerate(ctx.needs_input_grad[2:]):
+                if not need:
+                    grads[i] = None
+            return (dx if ctx.needs_input_grad[0] else None, None, *grads)
         meta, params, saved = ctx.meta, ctx.params, ctx.saved
         L, H = meta.L, meta.H
         B, S, D = ctx.shape
         M = B * S
         p, seed = ctx.p, ctx.seed
-        g = gout if (gout.dtype == torch.float32 and gout.is_contiguous()) else gout.float().contiguous()
         gs = g.view(M, D)
         _, dbranch, _, _ = ops.add_layernorm_bwd(None, None, None, None, None, gs, want_dx=False,
                                                  want_dbranch=True, dropout_p=p, seed=seed,

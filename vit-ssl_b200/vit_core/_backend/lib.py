@@ -35,6 +35,8 @@ SIGNATURES["vitssl_attention_fwd"] = "ppp" + "lll" + "pl" + "p" + "llll" + "f" +
 SIGNATURES["vitssl_attention_bwd"] = "ppp" + "lll" + "ppl" + "p" + "pl" + "pl" + "pl" + "llll" + "f" + "s"
 SIGNATURES["vitssl_attention_generic_fwd"] = "ppp" + "p" + "ppp" + "lllll" + "f" + "s"
 SIGNATURES["vitssl_attention_generic_bwd"] = "ppp" + "p" + "pp" + "p" + "ppp" + "lllll" + "f" + "s"
+SIGNATURES["vitssl_encoder_stack_fwd"] = "ps"
+SIGNATURES["vitssl_encoder_stack_bwd"] = "ps"
 SIGNATURES["vitssl_multi_cast_bf16"] = "pppis"
 SIGNATURES["vitssl_multi_ema"] = "pppifs"
 SIGNATURES["vitssl_colsum_bf16"] = "plllps"

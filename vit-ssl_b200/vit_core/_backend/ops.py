@@ -445,3 +445,136 @@ def dino_loss_bwd(teacher, student, center, t_stats, s_lse, grad_out, teacher_te
     _l.call("vitssl_dino_loss_bwd", _p(teacher), _p(student), _p(center), _p(t_stats), _p(s_lse), _p(go),
             _p(dstudent), G, V, B, K, float(teacher_temp), float(student_temp), _l.stream_ptr())
     return dstudent
+
+
+# ----------------------------------------------------------------------------------------
+# whole encoder stack in one C call (vitssl_encoder_stack_fwd / _bwd)
+# ----------------------------------------------------------------------------------------
+import ctypes as _ct
+
+_PP = _ct.POINTER(_ct.c_void_p)
+
+
+class _EncFwdArgs(_ct.Structure):
+    _fields_ = ([(n, _ct.c_int64) for n in ("B", "S", "D", "H", "F", "L")]
+                + [("dropout_p", _ct.c_float), ("eps", _ct.c_float), ("seed", _ct.c_uint64),
+                   ("x_in", _ct.c_void_p), ("out", _ct.c_void_p), ("y1", _ct.c_void_p), ("y2", _ct.c_void_p * 2)]
+                + [(n, _PP) for n in ("wqkv", "wo", "w1", "w2", "b1", "b2", "g1", "be1", "g2", "be2",
+                                      "xs", "mean1", "rstd1", "xn1", "qkv", "ctx", "lse",
+                                      "xmid", "mean2", "rstd2", "xn2", "u", "h")])
+
+
+class _EncBwdArgs(_ct.Structure):
+    _fields_ = ([("fwd", _ct.POINTER(_EncFwdArgs)), ("gout", _ct.c_void_p), ("dx", _ct.c_void_p)]
+                + [(n, _ct.c_void_p) for n in ("dbranch", "du", "dxn", "dctx", "dqkv")]
+                + [("gs", _ct.c_void_p * 2)]
+                + [(n, _PP) for n in ("dwqkv", "dwo", "dw1", "db1", "dw2", "db2", "dg1", "dbe1", "dg2", "dbe2")])
+
+
+def _layer_ptrs(t, L, per_layer=True):
+    """ctypes array of L device pointers into tensor t: slice l of its first dim, or t itself."""
+    base = _p(t)
+    step = t.stride(0) * t.element_size() if per_layer else 0
+    return (_ct.c_void_p * L)(*[base + l * step for l in range(L)])
+
+
+def _list_ptrs(ts):
+    return (_ct.c_void_p * len(ts))(*[_p(t) for t in ts])
+
+
+def encoder_stack_supported(S, D, H):
+    return PROFILE is None and D == H * 64 and D % 8 == 0 and attention_supported(S, S, 64)
+
+
+class EncoderStackState:
+    """Buffers and the C argument block of one forward call (kept alive for its backward)."""
+    __slots__ = ("args", "keep", "dims")
+
+
+def encoder_stack_fwd(x, weights, params, H, p, seed, need_grad, eps=1e-5):
+    """x fp32 [B,S,D] contiguous; weights[l] = (wqkv, wo, w1, w2) bf16 shadows; params = flat list of
+    12 fp32 parameters per block (functional.block_params order). Returns (out fp32 [B,S,D], state)."""
+    _l.ensure_device()
+    B, S, D = x.shape
+    L = len(weights)
+    F_ = weights[0][2].shape[0]
+    M = B * S
+    dev = x.device
+    bf, f32 = torch.bfloat16, torch.float32
+    n = L if need_grad else 1          # saved activations: one slot per layer, or one reused slot
+    per = need_grad
+    xs = torch.empty((max(n - 1, 1), M, D), device=dev, dtype=f32)
+    stats = torch.empty((4, n, M), device=dev, dtype=f32)
+    xn1 = torch.empty((n, M, D), device=dev, dtype=bf)
+    qkv = torch.empty((n, M, 3 * D), device=dev, dtype=bf)
+    ctx = torch.empty((n, M, D), device=dev, dtype=bf)
+    lse = torch.empty((n, B * H * S), device=dev, dtype=f32)
+    xmid = torch.empty((n, M, D), device=dev, dtype=f32)
+    xn2 = torch.empty((n, M, D), device=dev, dtype=bf)
+    uh = torch.empty((2, n, M, F_), device=dev, dtype=bf)
+    ytmp = torch.empty((3, M, D), device=dev, dtype=bf)
+    out = torch.empty((B, S, D), device=dev, dtype=f32)
+    a = _EncFwdArgs()
+    a.B, a.S, a.D, a.H, a.F, a.L = B, S, D, H, F_, L
+    a.dropout_p, a.eps, a.seed = float(p), float(eps), int(seed)
+    a.x_in, a.out = _p(x), _p(out)
+    a.y1 = _p(ytmp[0])
+    a.y2[0], a.y2[1] = _p(ytmp[1]), _p(ytmp[2])
+    keep = [x, out, xs, stats, xn1, qkv, ctx, lse, xmid, xn2, uh, ytmp, weights, params]
+    arrays = {}
+    for i, name in enumerate(("wqkv", "wo", "w1", "w2")):
+        arrays[name] = _list_ptrs([w[i] for w in weights])
+    for i, name in ((5, "b1"), (7, "b2"), (8, "g1"), (9, "be1"), (10, "g2"), (11, "be2")):
+        arrays[name] = _list_ptrs([params[12 * l + i] for l in range(L)])
+    # xs[l] for l >= 1 lives in slot l-1 (layer 0 reads x_in)
+    xs_base, xs_step = _p(xs), (xs.stride(0) * 4 if per else 0)
+    arrays["xs"] = (_ct.c_void_p * L)(*[xs_base + max(l - 1, 0) * xs_step for l in range(L)])
+    for i, name in enumerate(("mean1", "rstd1", "mean2", "rstd2")):
+        arrays[name] = _layer_ptrs(stats[i], L, per)
+    for name, t in (("xn1", xn1), ("qkv", qkv), ("ctx", ctx), ("lse", lse), ("xmid", xmid), ("xn2", xn2),
+                    ("u", uh[0]), ("h", uh[1])):
+        arrays[name] = _layer_ptrs(t, L, per)
+    for name, arr in arrays.items():
+        setattr(a, name, _ct.cast(arr, _PP))
+    keep.append(arrays)
+    _l.call("vitssl_encoder_stack_fwd", _ct.addressof(a), _l.stream_ptr())
+    st = EncoderStackState()
+    st.args, st.keep, st.dims = a, keep, (B, S, D, H, F_, L)
+    return out, st
+
+
+def encoder_stack_last_qkv(st):
+    """bf16 [B,S,3D] fused QKV activations of the LAST block (return_attn=True path)."""
+    B, S, D, H, F_, L = st.dims
+    qkv = st.keep[5]
+    return qkv[qkv.shape[0] - 1].view(B, S, 3 * D)
+
+
+def encoder_stack_bwd(st, gout):
+    """gout fp32 [B,S,D] contiguous -> (dx fp32 [B,S,D], per-layer gradient tensors dict)."""
+    B, S, D, H, F_, L = st.dims
+    M = B * S
+    dev = gout.device
+    bf, f32 = torch.bfloat16, torch.float32
+    dx = torch.empty((B, S, D), device=dev, dtype=f32)
+    tmp_d = torch.empty((3, M, D), device=dev, dtype=bf)        # dbranch, dxn, dctx
+    du = torch.empty((M, F_), device=dev, dtype=bf)
+    dqkv = torch.empty((M, 3 * D), device=dev, dtype=bf)
+    gs = torch.empty((2, M, D), device=dev, dtype=f32)
+    g = {"dwqkv": torch.empty((L, 3 * D, D), device=dev, dtype=f32), "dwo": torch.empty((L, D, D), device=dev, dtype=f32),
+         "dw1": torch.empty((L, F_, D), device=dev, dtype=f32), "db1": torch.empty((L, F_), device=dev, dtype=f32),
+         "dw2": torch.empty((L, D, F_), device=dev, dtype=f32), "db2": torch.empty((L, D), device=dev, dtype=f32)}
+    ln = torch.empty((4, L, D), device=dev, dtype=f32)
+    for i, name in enumerate(("dg1", "dbe1", "dg2", "dbe2")):
+        g[name] = ln[i]
+    b = _EncBwdArgs()
+    b.fwd = _ct.pointer(st.args)
+    b.gout, b.dx = _p(gout), _p(dx)
+    b.dbranch, b.dxn, b.dctx = _p(tmp_d[0]), _p(tmp_d[1]), _p(tmp_d[2])
+    b.du, b.dqkv = _p(du), _p(dqkv)
+    b.gs[0], b.gs[1] = _p(gs[0]), _p(gs[1])
+    arrays = {name: _layer_ptrs(t, L) for name, t in g.items()}
+    for name, arr in arrays.items():
+        setattr(b, name, _ct.cast(arr, _PP))
+    _l.call("vitssl_encoder_stack_bwd", _ct.addressof(b), _l.stream_ptr())
+    return dx, g
