@@ -72,7 +72,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
       mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1);
-      mbar_init(bar_p, 128); mbar_init(bar_o, 1); mbar_init(bar_oread, 128);
+      mbar_init(bar_p, 4); mbar_init(bar_o, 1); mbar_init(bar_oread, 4);
       fence_barrier_init();
     }
     __syncwarp();
@@ -199,7 +199,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);  // one arrival per warp
       float sum;
       {
         float s0, s1;
@@ -218,7 +219,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tmem_ld_32x32(lane_addr + FWD_COL_O + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(bar_oread);  // O is in registers: the next item's S MMA may overwrite TMEM
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_oread);  // O is in registers: the next item's S MMA may overwrite TMEM
         if (qrow < p.Sq) {
           __nv_bfloat16* op = p.out + (static_cast<long long>(b) * p.Sq + qrow) * p.ldo + h * 64;
 #pragma unroll
@@ -266,7 +268,8 @@ struct AttnBwdParams {
   float scale;
 };
 
-constexpr int BWD_THREADS = 288;
+constexpr int BWD_MATH_WARPS = 16;  // 4 per TMEM lane quadrant, 32 of the 128 key columns each
+constexpr int BWD_THREADS = 32 * BWD_MATH_WARPS + 32;
 constexpr int BWD_SMEM_Q = 0;          // 2 x 16 KB
 constexpr int BWD_SMEM_DO = 32768;     // 2 x 16 KB
 constexpr int BWD_SMEM_K = 65536;      // 2 x 16 KB
@@ -279,7 +282,7 @@ constexpr int BWD_SMEM_BYTES = BWD_SMEM_BAR + 128 + 1024;
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmap_o, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -289,19 +292,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bar_pds_ready = bar + 2;
   uint64_t* bar_pds_free = bar + 3;
   uint64_t* bar_dkv_free = bar + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 5);
+  uint64_t* bar_sdp_read = bar + 5;  // S / dP of the current iteration are in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
   const int nq = (p.Sq + 127) / 128, nk = (p.Sk + 127) / 128;  // each <= 2
   const int nit = nq * nk;
 
-  if (warp == 8) {
+  if (warp == BWD_MATH_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k);
-      tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
-      mbar_init(bar_load, 1); mbar_init(bar_sdp_full, 1); mbar_init(bar_pds_ready, 256);
-      mbar_init(bar_pds_free, 1); mbar_init(bar_dkv_free, 256);
+      tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_o);
+      mbar_init(bar_load, 1); mbar_init(bar_sdp_full, 1); mbar_init(bar_pds_ready, BWD_MATH_WARPS);
+      mbar_init(bar_pds_free, 1); mbar_init(bar_dkv_free, BWD_MATH_WARPS);
+      mbar_init(bar_sdp_read, BWD_MATH_WARPS);
       fence_barrier_init();
     }
     __syncwarp();
@@ -313,12 +318,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
 
-  if (warp == 8) {
+  if (warp == BWD_MATH_WARPS) {
     if (lane == 0) {
-      mbar_expect_tx(bar_load, static_cast<uint32_t>(2 * nq + 2 * nk) * 16384u);
+      mbar_expect_tx(bar_load, static_cast<uint32_t>(3 * nq + 2 * nk) * 16384u);
       for (int i = 0; i < nq; ++i) {
         tma_load_3d(smem + BWD_SMEM_Q + i * 16384, &tmap_q, bar_load, h * 64, i * 128, b);
         tma_load_3d(smem + BWD_SMEM_DO + i * 16384, &tmap_do, bar_load, h * 64, i * 128, b);
+        // O only feeds delta = rowsum(O * dO); it borrows the P region, which is idle until then
+        tma_load_3d(smem + BWD_SMEM_P + i * 16384, &tmap_o, bar_load, h * 64, i * 128, b);
       }
       for (int j = 0; j < nk; ++j) {
         tma_load_3d(smem + BWD_SMEM_K + j * 16384, &tmap_k, bar_load, h * 64, j * 128, b);
@@ -376,132 +383,145 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else {
-    // 256 math threads: row r = TMEM lane, `half` selects 64 of the 128 key columns
+    // 512 math threads: row r = TMEM lane, `cq` selects 32 of the 128 key columns of the tile
     const int t = threadIdx.x;
-    const int r = t & 127, half = t >> 7;
+    const int r = t & 127, cq = t >> 7;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const float sl2 = p.scale * kLog2e;
     float delta0 = 0.f, delta1 = 0.f, nlse0 = 0.f, nlse1 = 0.f;
     bool qvalid0 = false, qvalid1 = false;
+    mbar_wait(bar_load, 0);
+    // delta_i = sum_d O[i, d] * dO[i, d] from the TMA-staged (128B-swizzled) tiles in shared memory
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int qrow = i * 128 + r;
       const bool valid = i < nq && qrow < p.Sq;
       if (i == 0) qvalid0 = valid; else qvalid1 = valid;
       if (valid) {
-        const long long off = (static_cast<long long>(b) * p.Sq + qrow) * p.ldo + h * 64;
-        const uint4* po = reinterpret_cast<const uint4*>(p.o + off);
-        const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + off);
-        float acc = 0.f;
+        const uint8_t* so = smem + BWD_SMEM_P + i * 16384 + r * 128;
+        const uint8_t* sd = smem + BWD_SMEM_DO + i * 16384 + r * 128;
+        f32x2 acc2 = pk2(0.f, 0.f);
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
-          const uint4 a = po[v], d = pd[v];
-          acc += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x);
-          acc += bf16_lo(a.y) * bf16_lo(d.y) + bf16_hi(a.y) * bf16_hi(d.y);
-          acc += bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z);
-          acc += bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+          const int sw = (v ^ (r & 7)) << 4;
+          const uint4 a = *reinterpret_cast<const uint4*>(so + sw);
+          const uint4 d = *reinterpret_cast<const uint4*>(sd + sw);
+          acc2 = ffma2(pk2(bf16_lo(a.x), bf16_hi(a.x)), pk2(bf16_lo(d.x), bf16_hi(d.x)), acc2);
+          acc2 = ffma2(pk2(bf16_lo(a.y), bf16_hi(a.y)), pk2(bf16_lo(d.y), bf16_hi(d.y)), acc2);
+          acc2 = ffma2(pk2(bf16_lo(a.z), bf16_hi(a.z)), pk2(bf16_lo(d.z), bf16_hi(d.z)), acc2);
+          acc2 = ffma2(pk2(bf16_lo(a.w), bf16_hi(a.w)), pk2(bf16_lo(d.w), bf16_hi(d.w)), acc2);
         }
+        float a0, a1;
+        upk2(acc2, a0, a1);
         const float nl = -p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qrow] * kLog2e;
-        if (i == 0) { delta0 = acc; nlse0 = nl; } else { delta1 = acc; nlse1 = nl; }
+        if (i == 0) { delta0 = a0 + a1; nlse0 = nl; } else { delta1 = a0 + a1; nlse1 = nl; }
       }
     }
-    uint8_t* sP = smem + BWD_SMEM_P + half * 16384 + r * 128;
-    uint8_t* sDS = smem + BWD_SMEM_DS + half * 16384 + r * 128;
+    // every math thread has read O before anyone overwrites the region with P
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * BWD_MATH_WARPS) : "memory");
+    // this thread's 4 x 16-byte chunks (32 keys) inside key block (cq >> 1) of the P / dS tiles
+    uint8_t* sP = smem + BWD_SMEM_P + (cq >> 1) * 16384 + r * 128;
+    uint8_t* sDS = smem + BWD_SMEM_DS + (cq >> 1) * 16384 + r * 128;
 
     for (int it = 0; it < nit; ++it) {
       const int j = it / nq, i = it % nq;
       mbar_wait(bar_sdp_full, it & 1);
       tc_fence_after();
-      if (it > 0) mbar_wait(bar_pds_free, (it - 1) & 1);  // previous P / dS consumed by the MMAs
       // invalid query rows recompute p = 2^(-inf) = 0 (their S rows are zero: TMA zero-fills Q)
       const bool rv = i ? qvalid1 : qvalid0;
       const float dl = i ? delta1 : delta0, nl = rv ? (i ? nlse1 : nlse0) : -INFINITY;
       const f32x2 sl2v = pk2(sl2, sl2), nlv = pk2(nl, nl), ndlv = pk2(-dl, -dl);
+      uint32_t pp[2][8], dd[2][8];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int key0 = j * 128 + half * 64 + c * 32;
-        uint32_t pp[16], dd[16];
+      for (int c = 0; c < 2; ++c) {  // two sub-chunks of 16 keys
+        const int key0 = j * 128 + cq * 32 + c * 16;
         if (key0 < p.Sk) {
-          uint32_t s[32], dp[32];
+          uint32_t sv[16], dp[16];
           __syncwarp();
-          tmem_ld_32x32(lane_addr + COL_S + half * 64 + c * 32, s);
-          tmem_ld_32x32(lane_addr + COL_DP + half * 64 + c * 32, dp);
+          tmem_ld_32x16(lane_addr + COL_S + cq * 32 + c * 16, sv);
+          tmem_ld_32x16(lane_addr + COL_DP + cq * 32 + c * 16, dp);
           tmem_ld_wait();
-          const bool full = key0 + 32 <= p.Sk;
+          const bool full = key0 + 16 <= p.Sk;
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < 16; e += 2) {
             float a0, a1;
-            upk2(ffma2(pk2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), sl2v, nlv), a0, a1);
+            upk2(ffma2(pk2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2v, nlv), a0, a1);
             float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
             if (!full) {
               p0 = (key0 + e < p.Sk) ? p0 : 0.f;
               p1 = (key0 + e + 1 < p.Sk) ? p1 : 0.f;
             }
-            pp[e >> 1] = pack_bf16(p0, p1);
+            pp[c][e >> 1] = pack_bf16(p0, p1);
             float d0, d1;  // dS = P * (dP - delta)
             upk2(fmul2(pk2(p0, p1), fadd2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ndlv)), d0, d1);
-            dd[e >> 1] = pack_bf16(d0, d1);
+            dd[c][e >> 1] = pack_bf16(d0, d1);
           }
         } else {  // key chunk entirely past Sk
 #pragma unroll
-          for (int e = 0; e < 16; ++e) pp[e] = dd[e] = 0u;
+          for (int e = 0; e < 8; ++e) pp[c][e] = dd[c][e] = 0u;
         }
+      }
+      // everything above overlapped the previous iteration's dV / dK / dQ MMAs; only the stores
+      // need their P / dS operands to have been consumed
+      if (it > 0) mbar_wait(bar_pds_free, (it - 1) & 1);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = c * 4 + g;
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int chunk = (cq & 1) * 4 + c * 2 + g;
           const int sw = (chunk ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pp[4 * g], pp[4 * g + 1], pp[4 * g + 2], pp[4 * g + 3]);
-          *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dd[4 * g], dd[4 * g + 1], dd[4 * g + 2], dd[4 * g + 3]);
+          *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pp[c][4 * g], pp[c][4 * g + 1], pp[c][4 * g + 2], pp[c][4 * g + 3]);
+          *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dd[c][4 * g], dd[c][4 * g + 1], dd[c][4 * g + 2], dd[c][4 * g + 3]);
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(bar_pds_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pds_ready);  // one arrival per warp
 
       if (i == nq - 1) {
-        // key tile j finished: drain dV_j (threads 0-127) / dK_j (threads 128-255)
+        // key tile j finished: warps 0-7 drain dV_j, warps 8-15 dK_j; 32 of the 64 columns each
         mbar_wait(bar_pds_free, it & 1);
         tc_fence_after();
         const int krow = j * 128 + r;
-        const uint32_t col = half == 0 ? COL_DV : COL_DK;
-        const float mul = half == 0 ? 1.0f : p.scale;
-        __nv_bfloat16* base = half == 0 ? p.dv : p.dk;
-        const long long ld = half == 0 ? p.lddv : p.lddk;
+        const int sel = cq >> 1, cc = cq & 1;
+        const uint32_t col = (sel == 0 ? COL_DV : COL_DK) + cc * 32;
+        const float mul = sel == 0 ? 1.0f : p.scale;
+        __nv_bfloat16* base = sel == 0 ? p.dv : p.dk;
+        const long long ld = sel == 0 ? p.lddv : p.lddk;
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(lane_addr + col, v);
+        tmem_ld_wait();
+        if (krow < p.Sk) {
+          __nv_bfloat16* op = base + (static_cast<long long>(b) * p.Sk + krow) * ld + h * 64 + cc * 32;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld_32x32(lane_addr + col + c * 32, v);
-          tmem_ld_wait();
-          if (krow < p.Sk) {
-            __nv_bfloat16* op = base + (static_cast<long long>(b) * p.Sk + krow) * ld + h * 64 + c * 32;
-#pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-              uint4 o;
-              o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
-              o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
-              o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
-              o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
-              *reinterpret_cast<uint4*>(op + e) = o;
-            }
+          for (int e = 0; e < 32; e += 8) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
+            o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
+            o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
+            o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
+            *reinterpret_cast<uint4*>(op + e) = o;
           }
         }
         tc_fence_before();
-        mbar_arrive(bar_dkv_free);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dkv_free);
       }
     }
-    // dQ_i: threads 0-127 drain tile 0, threads 128-255 tile 1 (all MMAs retired: last
-    // bar_pds_free phase was waited on above)
-    if (half < nq) {
-      const int qrow = half * 128 + r;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+    // dQ: thread group cq drains columns (cq & 1) * 32 .. +32 of query tile cq >> 1 (all MMAs have
+    // retired: the last bar_pds_free phase was waited on above)
+    {
+      const int tile = cq >> 1, cc = cq & 1;
+      if (tile < nq) {
+        const int qrow = tile * 128 + r;
         uint32_t v[32];
         __syncwarp();
-        tmem_ld_32x32(lane_addr + COL_DQ + half * 64 + c * 32, v);
+        tmem_ld_32x32(lane_addr + COL_DQ + tile * 64 + cc * 32, v);
         tmem_ld_wait();
         if (qrow < p.Sq) {
-          __nv_bfloat16* op = p.dq + (static_cast<long long>(b) * p.Sq + qrow) * p.lddq + h * 64 + c * 32;
+          __nv_bfloat16* op = p.dq + (static_cast<long long>(b) * p.Sq + qrow) * p.lddq + h * 64 + cc * 32;
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             uint4 o;
@@ -517,7 +537,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == BWD_MATH_WARPS) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -713,12 +733,13 @@ extern "C" int vitssl_attention_bwd(const void* q, const void* k, const void* v,
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.lddk = lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.lddv = lddv;
   p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk; p.scale = scale;
-  CUtensorMap mq, mk, mv, mdo;
+  CUtensorMap mq, mk, mv, mdo, mo;
   int rc;
   if ((rc = make_head_map(&mq, q, p.B, p.Sq, p.H, ldq, 128))) return rc;
   if ((rc = make_head_map(&mk, k, p.B, p.Sk, p.H, ldk, 128))) return rc;
   if ((rc = make_head_map(&mv, v, p.B, p.Sk, p.H, ldv, 128))) return rc;
   if ((rc = make_head_map(&mdo, d_out, p.B, p.Sq, p.H, ldo, 128))) return rc;
+  if ((rc = make_head_map(&mo, out, p.B, p.Sq, p.H, ldo, 128))) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
@@ -726,7 +747,7 @@ extern "C" int vitssl_attention_bwd(const void* q, const void* k, const void* v,
     configured = true;
   }
   dim3 grid((unsigned)H, (unsigned)B);
-  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(mq, mk, mv, mdo, p);
+  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(mq, mk, mv, mdo, mo, p);
   return check_launch("attention_bwd");
 }
 
