@@ -36,7 +36,7 @@ int vitssl_version(void);              /* major*10000 + minor*100 + patch */
 const char* vitssl_last_error(void);   /* thread-local, never NULL */
 int vitssl_device_check(void);         /* 0 iff the current device is sm_100 (B200) */
 int vitssl_num_sms(void);
-/* number of kernels this library has launched on the calling thread since the last reset
+/* number of kernels this library has launched (all threads of the process) since the last reset
  * (bench.py reports it as gpu_launches) */
 int64_t vitssl_launch_count(int reset);
 

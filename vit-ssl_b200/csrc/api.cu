@@ -2,6 +2,8 @@
 // host-side TMA descriptor encoding (driver entry point resolved at run time, so the library
 // links against cudart only).
 #include <cudaTypedefs.h>
+
+#include <atomic>
 #include <stdarg.h>
 #include <string.h>
 
@@ -11,7 +13,8 @@
 namespace vitssl {
 
 static thread_local char g_error[512] = "";
-static thread_local long long g_launches = 0;
+// process-wide: backward kernels are launched from autograd's worker thread
+static std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -112,8 +115,8 @@ extern "C" const char* vitssl_last_error(void) { return vitssl::g_error; }
 extern "C" int vitssl_num_sms(void) { return vitssl::num_sms(); }
 
 extern "C" int64_t vitssl_launch_count(int reset) {
-  const long long v = vitssl::g_launches;
-  if (reset) vitssl::g_launches = 0;
+  const long long v = vitssl::g_launches.load();
+  if (reset) vitssl::g_launches.store(0);
   return v;
 }
 
