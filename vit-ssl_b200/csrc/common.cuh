@@ -87,8 +87,11 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint
   uint32_t c2 = static_cast<uint32_t>(offset), c3 = static_cast<uint32_t>(offset >> 32);
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t hi0, lo0, hi1, lo1;  // one IMAD.WIDE.U32 per product
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(0xD2511F53u));
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(0xCD9E8D57u));
     const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
@@ -127,6 +130,19 @@ __device__ __forceinline__ void dropout_scale8(uint64_t seed, uint64_t offset, u
   m[5] = (r.z >= th) ? scale : 0.0f;
   m[6] = ((r.w << 16) >= th) ? scale : 0.0f;
   m[7] = (r.w >= th) ? scale : 0.0f;
+}
+
+// Lane-mask form used by the GEMM epilogues (their dropout site is private to the GELU GEMM pair,
+// so its rule may differ from the LayerNorm sites): element e keeps iff (u16 & 0x7fff) >= th15,
+// th15 = p * 32768. For a Philox word holding two elements the test runs on both 16-bit lanes at
+// once: with the lanes' top bits forced to 1 the subtraction cannot borrow across lanes and
+// leaves each lane's top bit set iff that lane passes; PRMT's sign-replicate mode then widens the
+// bit to 0xffff, which is ANDed onto the packed bf16x2 result. th2 = th15 * 0x10001.
+__device__ __forceinline__ uint32_t dropout_lane_mask2(uint32_t r, uint32_t th2) {
+  const uint32_t t = (r | 0x80008000u) - th2;
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(t));  // bytes {1s,1s,3s,3s}: s = sign replicate
+  return m;
 }
 
 // ----------------------------------------------------------------------------------
@@ -221,6 +237,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// Same, for the single-thread producer / MMA-issuer roles: the try_wait carries a suspend-time
+// hint so a waiting warp parks in hardware instead of burning issue slots of the epilogue warps
+// that share its scheduler (it still wakes as soon as the phase completes).
+__device__ __forceinline__ bool mbar_try_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_parked(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_parked(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("vitssl: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t cta_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cta_addr) : "memory");
 }
 
 // ----------------------------------------------------------------------------------

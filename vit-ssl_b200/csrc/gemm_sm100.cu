@@ -29,12 +29,12 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes half of the tile's columns
+constexpr int EPI_WARPS = 16;  // four per TMEM lane quadrant: 32-column chunks are dealt round-robin
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int STG_BUF_BYTES = 4096;                       // one 32x32 fp32 chunk, or bf16 C + bf16 aux
-constexpr int STG_BYTES = EPI_WARPS * 2 * STG_BUF_BYTES;  // double-buffered per epilogue warp
-constexpr int SMEM_LIMIT = 232448;                        // 227 KB per CTA
+constexpr int STG_BUF_BYTES = 4096;                   // one 32x32 fp32 chunk, or bf16 C + bf16 aux
+constexpr int STG_BYTES = EPI_WARPS * STG_BUF_BYTES;  // one private staging tile per epilogue warp
+constexpr int SMEM_LIMIT = 232448;                    // 227 KB per CTA
 
 struct GemmShape {
   int M, N, K;
@@ -54,7 +54,7 @@ struct GemmEpi {
   int atomic;    // 1: red.add.f32 into C (split-K)
   int vec_ok;    // C rows are 16-byte aligned -> vector stores in the direct epilogue
   int tma_out;   // 1: epilogue goes through staging + TMA store (tmap_c / tmap_aux valid)
-  uint32_t drop_thresh16;
+  uint32_t drop_th2;  // (p * 32768) * 0x10001, 0 = no dropout (common.cuh: dropout_lane_mask2)
   float drop_scale;
   unsigned long long seed, offset;
 };
@@ -83,94 +83,110 @@ struct TileCtx {
   int worker, nworkers;   // tile-loop start and stride (CTAs, or CTA pairs)
   int tile_rows;          // rows of one scheduled tile: 128, or 256 for a pair
   int row_off;            // this CTA's first row inside the tile (rank * 128)
-  uint32_t tempty_addr;   // shared::cluster address of tempty_bar[0] in the CTA that issues the MMAs
+  uint32_t tempty_addr;   // address of tempty_bar[0] in the CTA that issues the MMAs
+  bool pair;              // tempty_addr is a shared::cluster address (the leader may be the peer)
 };
+// A cluster-scope release arrive costs a MEMBAR.ALL + ERRBAR per call (7 % of all stall samples of
+// the GELU GEMM in ncu); a single CTA only needs the CTA-scope form.
 __device__ __forceinline__ void tempty_arrive(const TileCtx& t, int acc) {
-  mbar_arrive_cluster(t.tempty_addr + acc * 8);
+  if (t.pair) mbar_arrive_cluster(t.tempty_addr + acc * 8);
+  else mbar_arrive_addr(t.tempty_addr + acc * 8);
 }
 
 // ---- epilogue math on one 32-column chunk of one accumulator row (all in registers) ----------
-// fp32 output (NONE / BIAS): v[] <- alpha * acc (+ bias)
-template <int MODE>
-__device__ __forceinline__ void epilogue_math_f32(float (&v)[32], const GemmEpi& e, int nb, int ncols) {
-  float b[32];
-  if constexpr (MODE == VITSSL_EPI_BIAS) {
-    if (ncols == 32) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + nb + i));
-        b[i] = t.x; b[i + 1] = t.y; b[i + 2] = t.z; b[i + 3] = t.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) b[i] = (i < ncols) ? __ldg(e.bias + nb + i) : 0.0f;
-    }
+__device__ __forceinline__ void load_bias8(const float* bias, int nb, int g, int ncols, float (&b)[8]) {
+  if (ncols == 32) {
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(bias + nb + 8 * g));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(bias + nb + 8 * g + 4));
+    b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
   } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) b[i] = 0.0f;
+    for (int i = 0; i < 8; ++i) b[i] = (8 * g + i < ncols) ? __ldg(bias + nb + 8 * g + i) : 0.0f;
   }
+}
+
+// fp32 output (NONE / BIAS): v[] <- alpha * acc (+ bias)
+template <int MODE>
+__device__ __forceinline__ void epilogue_math_f32(uint32_t (&v)[32], const GemmEpi& e, int nb, int ncols) {
   const f32x2 al = pk2(e.alpha, e.alpha);
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) upk2(ffma2(pk2(v[i], v[i + 1]), al, pk2(b[i], b[i + 1])), v[i], v[i + 1]);
+  for (int g = 0; g < 4; ++g) {
+    float b[8];
+    if constexpr (MODE == VITSSL_EPI_BIAS) {
+      load_bias8(e.bias, nb, g, ncols, b);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b[i] = 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const int i = 8 * g + j;
+      float x0, x1;
+      upk2(ffma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), al, pk2(b[j], b[j + 1])), x0, x1);
+      v[i] = __float_as_uint(x0);
+      v[i + 1] = __float_as_uint(x1);
+    }
+  }
 }
 
 // bf16 output: c[] <- packed bf16x2 of C. BIAS_GELU also produces u[] = packed bf16(alpha*acc+bias)
 // (the aux output, feed_forward.py:26 pre-activation); DGELU consumes u[].
 //   BIAS_GELU: C = dropout(u * Phi(u))          DGELU: C = alpha*acc * mask/(1-p) * (Phi(u) + u phi(u))
+// Dropout: the 1/(1-p) factor rides on a multiply that is there anyway and the keep decision is a
+// lane mask ANDed onto the packed bf16 pair (no per-element compare / select).
 template <int MODE>
-__device__ __forceinline__ void epilogue_math_bf16(const float (&v)[32], uint32_t (&c)[16], uint32_t (&u)[16],
+__device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint32_t (&c)[16], uint32_t (&u)[16],
                                                    const GemmEpi& e, const GemmShape& s, int row, int nb,
                                                    int ncols) {
-  float b[32];
-  if constexpr (MODE == VITSSL_EPI_BIAS || MODE == VITSSL_EPI_BIAS_GELU) {
-    if (ncols == 32) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + nb + i));
-        b[i] = t.x; b[i + 1] = t.y; b[i + 2] = t.z; b[i + 3] = t.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) b[i] = (i < ncols) ? __ldg(e.bias + nb + i) : 0.0f;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) b[i] = 0.0f;
-  }
   const f32x2 al = pk2(e.alpha, e.alpha);
   if constexpr (MODE == VITSSL_EPI_NONE || MODE == VITSSL_EPI_BIAS) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float x0, x1;
-      upk2(ffma2(pk2(v[i], v[i + 1]), al, pk2(b[i], b[i + 1])), x0, x1);
-      c[i >> 1] = pack_bf16(x0, x1);
+    for (int g = 0; g < 4; ++g) {
+      float b[8];
+      if constexpr (MODE == VITSSL_EPI_BIAS) {
+        load_bias8(e.bias, nb, g, ncols, b);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const int i = 8 * g + j;
+        float x0, x1;
+        upk2(ffma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), al, pk2(b[j], b[j + 1])), x0, x1);
+        c[i >> 1] = pack_bf16(x0, x1);
+      }
     }
   } else {
-    const bool drop = e.drop_thresh16 != 0;
+    const bool drop = e.drop_th2 != 0;
+    const float sc = drop ? e.drop_scale : 1.0f;
+    const f32x2 scv = MODE == VITSSL_EPI_DGELU ? pk2(sc * e.alpha, sc * e.alpha) : pk2(sc, sc);
     const unsigned long long g8 =
         (static_cast<unsigned long long>(row) * s.N + nb) >> 3;  // N % 8 == 0 enforced when dropping
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      float m[8];
+      uint32_t keep[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
       if (drop) {
-        dropout_scale8(e.seed, e.offset, g8 + g, e.drop_thresh16, e.drop_scale, m);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = 1.0f;
+        const uint4 r = philox4x32<DROPOUT_PHILOX_ROUNDS>(e.seed, e.offset, g8 + g);
+        keep[0] = dropout_lane_mask2(r.x, e.drop_th2);
+        keep[1] = dropout_lane_mask2(r.y, e.drop_th2);
+        keep[2] = dropout_lane_mask2(r.z, e.drop_th2);
+        keep[3] = dropout_lane_mask2(r.w, e.drop_th2);
       }
+      float b[8];
+      if constexpr (MODE == VITSSL_EPI_BIAS_GELU) load_bias8(e.bias, nb, g, ncols, b);
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
         const int i = 8 * g + j;
         if constexpr (MODE == VITSSL_EPI_BIAS_GELU) {
           float x0, x1;
-          upk2(ffma2(pk2(v[i], v[i + 1]), al, pk2(b[i], b[i + 1])), x0, x1);
+          upk2(ffma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), al, pk2(b[j], b[j + 1])), x0, x1);
           const uint32_t up = pack_bf16(x0, x1);
           u[i >> 1] = up;
           const float u0 = bf16_lo(up), u1 = bf16_hi(up);
-          const f32x2 h = fmul2(fmul2(pk2(u0, u1), normal_cdf2(u0, u1)), pk2(m[j], m[j + 1]));
           float h0, h1;
-          upk2(h, h0, h1);
-          c[i >> 1] = pack_bf16(h0, h1);
+          upk2(fmul2(fmul2(pk2(u0, u1), scv), normal_cdf2(u0, u1)), h0, h1);
+          c[i >> 1] = pack_bf16(h0, h1) & keep[j >> 1];
         } else {
           const uint32_t up = u[i >> 1];
           const float u0 = bf16_lo(up), u1 = bf16_hi(up);
@@ -180,11 +196,10 @@ __device__ __forceinline__ void epilogue_math_bf16(const float (&v)[32], uint32_
           upk2(fmul2(fmul2(uu, uu), pk2(-0.72134752044448170f, -0.72134752044448170f)), a0, a1);
           const f32x2 pdf = pk2(ex2_approx(a0), ex2_approx(a1));
           const f32x2 upd = fmul2(fmul2(uu, pk2(0.3989422804014327f, 0.3989422804014327f)), pdf);
-          const f32x2 gp = ffma2(upd, pk2(1.0f, 1.0f), normal_cdf2(u0, u1));  // Phi + u phi
-          const f32x2 dv = fmul2(fmul2(fmul2(pk2(v[i], v[i + 1]), al), gp), pk2(m[j], m[j + 1]));
+          const f32x2 gp = fadd2(upd, normal_cdf2(u0, u1));  // Phi + u phi
           float d0, d1;
-          upk2(dv, d0, d1);
-          c[i >> 1] = pack_bf16(d0, d1);
+          upk2(fmul2(fmul2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), scv), gp), d0, d1);
+          c[i >> 1] = pack_bf16(d0, d1) & keep[j >> 1];
         }
       }
     }
@@ -206,125 +221,111 @@ __device__ __forceinline__ void stage_row_bf16(uint8_t* tile, int lane, const ui
   }
 }
 // 32 fp32 of row `lane` -> staging tile with rows of 128 bytes in the SWIZZLE_128B pattern
-__device__ __forceinline__ void stage_row_f32(uint8_t* tile, int lane, const float (&v)[32]) {
+__device__ __forceinline__ void stage_row_f32(uint8_t* tile, int lane, const uint32_t (&v)[32]) {
   const uint32_t base = smem_u32(tile) + lane * 128;
   const int sw = lane & 7;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint32_t a = base + ((j ^ sw) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__float_as_uint(v[4 * j])),
-                 "r"(__float_as_uint(v[4 * j + 1])), "r"(__float_as_uint(v[4 * j + 2])),
-                 "r"(__float_as_uint(v[4 * j + 3]))
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                 "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
                  : "memory");
   }
 }
-// inverse of stage_row_bf16: read row `lane` of a SWIZZLE_64B tile that TMA loaded
-__device__ __forceinline__ void unstage_row_bf16(const uint8_t* tile, int lane, uint32_t (&u)[16]) {
-  const uint32_t base = smem_u32(tile) + lane * 64;
-  const int sw = (lane >> 1) & 3;
+// DGELU operand: 32 saved pre-activations (bf16) of one row straight from global memory; each
+// thread reads one contiguous 64-byte segment (two full sectors), issued before the accumulator
+// wait so the latency hides behind it. Rows past M / columns past N read as 0.
+__device__ __forceinline__ void load_aux_row(const __nv_bfloat16* aux, long long ld, int row, int M, int nb,
+                                             int ncols, uint32_t (&u)[16]) {
+  if (row < M && ncols == 32) {
+    const uint4* p = reinterpret_cast<const uint4*>(aux + static_cast<long long>(row) * ld + nb);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(u[4 * j]), "=r"(u[4 * j + 1]), "=r"(u[4 * j + 2]), "=r"(u[4 * j + 3])
-                 : "r"(base + ((j ^ sw) << 4))
-                 : "memory");
+    for (int j = 0; j < 4; ++j) {
+      const uint4 t = __ldg(p + j);
+      u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
+    }
+  } else {
+    const unsigned short* p = reinterpret_cast<const unsigned short*>(aux) + static_cast<long long>(row) * ld + nb;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t lo = (row < M && 2 * i < ncols) ? __ldg(p + 2 * i) : 0u;
+      const uint32_t hi = (row < M && 2 * i + 1 < ncols) ? __ldg(p + 2 * i + 1) : 0u;
+      u[i] = lo | (hi << 16);
+    }
   }
 }
 
 // ---- staged epilogue of one warp over its share of the persistent tile loop -------------------
-// The warp owns TMEM lanes [32q, 32q+32) and the 32-column chunks [half*NC/2, (half+1)*NC/2).
+// The warp owns TMEM lanes [32q, 32q+32) and the 32-column chunks cg, cg+4, ... of every tile.
+// Four warps per scheduler give the chunk math (several hundred dependent ALU/FMA instructions
+// for the GELU forms) the thread-level parallelism it needs; each warp stages one chunk at a
+// time in a private 4 KB tile and hands it to a TMA store.
 template <int BN, int MODE, bool OUT_F32>
 __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const CUtensorMap* tmap_aux,
                                                 const GemmShape& s, const GemmEpi& e, uint8_t* stg,
-                                                uint64_t* aux_bar, uint64_t* tfull_bar,
-                                                const TileCtx& tc, uint32_t tmem_base, int q,
-                                                int half, int lane) {
+                                                uint64_t* tfull_bar, const TileCtx& tc,
+                                                uint32_t tmem_base, int q, int cg, int lane) {
   static_assert(!(OUT_F32 && (MODE == VITSSL_EPI_BIAS_GELU || MODE == VITSSL_EPI_DGELU)),
                 "GELU epilogues write bf16");
-  constexpr int CHUNKS_PER_WARP = BN / 32 / (EPI_WARPS / 4);
+  constexpr int NC = BN / 32;
   const int num_work = s.m_tiles * s.n_tiles * s.splits;
   int acc = 0;
   uint32_t acc_phase = 0;
-  uint32_t cc = 0;  // chunks processed so far: staging buffer = cc & 1, its barrier parity = (cc >> 1) & 1
   for (int w = tc.worker; w < num_work; w += tc.nworkers) {
     const int n_blk = w % s.n_tiles;
     const int m_blk = (w / s.n_tiles) % s.m_tiles;
-    const int m0 = m_blk * tc.tile_rows + tc.row_off;
-    const int n0 = n_blk * BN + half * CHUNKS_PER_WARP * 32;  // first column of this warp's share
-    const int row0 = m0 + q * 32;
-    const int nvalid = max(0, min(CHUNKS_PER_WARP * 32, s.N - n0));
-    const int nchunks = (nvalid + 31) >> 5;
-    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN +
-                          half * CHUNKS_PER_WARP * 32;
+    const int row0 = m_blk * tc.tile_rows + tc.row_off + q * 32;
+    const int nbase = n_blk * BN;
+    const int nch = min(NC, (s.N - nbase + 31) >> 5);  // chunks of this tile that hold columns < N
+    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-    if constexpr (MODE == VITSSL_EPI_DGELU) {
-      if (lane == 0 && nchunks > 0) {  // pre-activation chunk 0: in flight while the MMAs finish
-        mbar_expect_tx(&aux_bar[cc & 1], 2048);
-        tma_load_2d(stg + (cc & 1) * STG_BUF_BYTES + 2048, tmap_aux, &aux_bar[cc & 1], n0, row0);
-      }
+    uint32_t up[16];
+    if constexpr (MODE == VITSSL_EPI_DGELU) {  // first chunk's pre-activations: in flight while the MMAs finish
+      if (cg < nch) load_aux_row(e.aux, e.ld_aux, row0 + lane, s.M, nbase + cg * 32, min(32, s.N - nbase - cg * 32), up);
     }
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
     __syncwarp();
-    if (nchunks == 0) {
+    if (cg >= nch) {
       tc_fence_before();
       if (lane == 0) tempty_arrive(tc, acc);
     }
-
-    uint32_t ra[32], rb[32];
-    if (nchunks > 0) tmem_ld_32x32(tcol, ra);
-
-    auto step = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
-      tmem_ld_wait();  // `cur` has landed
-      __syncwarp();
-      if (c + 1 < nchunks) {
-        tmem_ld_32x32(tcol + (c + 1) * 32, nxt);
-      } else {  // this warp's columns are all in registers: hand the TMEM buffer back
+#pragma unroll 1
+    for (int c = cg; c < nch; c += 4) {
+      const int nb = nbase + c * 32;
+      const int ncols = min(32, s.N - nb);
+      uint32_t r[32];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the single-lane sections
+      tmem_ld_32x32(tcol + c * 32, r);
+      if constexpr (MODE == VITSSL_EPI_DGELU) {
+        if (c != cg) load_aux_row(e.aux, e.ld_aux, row0 + lane, s.M, nb, ncols, up);
+      }
+      tmem_ld_wait();
+      if (c + 4 >= nch) {  // this warp's columns are all in registers: hand the TMEM buffer back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) tempty_arrive(tc, acc);
       }
-      const int nb = n0 + c * 32;
-      const int ncols = min(32, s.N - nb);
-      uint8_t* buf = stg + (cc & 1) * STG_BUF_BYTES;
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cur[i]);
       if constexpr (OUT_F32) {
-        epilogue_math_f32<MODE>(v, e, nb, ncols);
-        if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer two chunks ago
+        epilogue_math_f32<MODE>(r, e, nb, ncols);
+        if (lane == 0) tma_store_wait_read<0>();  // the previous chunk's store has drained the tile
         __syncwarp();
-        stage_row_f32(buf, lane, v);
+        stage_row_f32(stg, lane, r);
       } else {
-        uint32_t cp[16], up[16];
-        if constexpr (MODE == VITSSL_EPI_DGELU) {
-          if (lane == 0 && c + 1 < nchunks) {  // next chunk's pre-activations into the other buffer
-            const uint32_t nc = cc + 1;       // (its last readers passed the __syncwarp above)
-            mbar_expect_tx(&aux_bar[nc & 1], 2048);
-            tma_load_2d(stg + (nc & 1) * STG_BUF_BYTES + 2048, tmap_aux, &aux_bar[nc & 1], nb + 32, row0);
-          }
-          mbar_wait(&aux_bar[cc & 1], (cc >> 1) & 1);
-          unstage_row_bf16(buf + 2048, lane, up);
-        }
-        epilogue_math_bf16<MODE>(v, cp, up, e, s, row0 + lane, nb, ncols);
-        if (lane == 0) tma_store_wait_read<1>();
+        uint32_t cp[16];
+        epilogue_math_bf16<MODE>(r, cp, up, e, s, row0 + lane, nb, ncols);
+        if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
-        stage_row_bf16(buf, lane, cp);
-        if constexpr (MODE == VITSSL_EPI_BIAS_GELU) stage_row_bf16(buf + 2048, lane, up);
+        stage_row_bf16(stg, lane, cp);
+        if constexpr (MODE == VITSSL_EPI_BIAS_GELU) stage_row_bf16(stg + 2048, lane, up);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(tmap_c, buf, nb, row0);
-        if constexpr (MODE == VITSSL_EPI_BIAS_GELU) tma_store_2d(tmap_aux, buf + 2048, nb, row0);
+        tma_store_2d(tmap_c, stg, nb, row0);
+        if constexpr (MODE == VITSSL_EPI_BIAS_GELU) tma_store_2d(tmap_aux, stg + 2048, nb, row0);
         tma_store_commit();
       }
-      ++cc;
-    };
-#pragma unroll 1
-    for (int c = 0; c < nchunks; c += 2) {
-      step(ra, rb, c);
-      if (c + 1 < nchunks) step(rb, ra, c + 1);
     }
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
@@ -337,8 +338,8 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
 template <int BN>
 __device__ __forceinline__ void epilogue_direct(const GemmShape& s, const GemmEpi& e,
                                                 uint64_t* tfull_bar, const TileCtx& tc,
-                                                uint32_t tmem_base, int q, int half, int lane) {
-  constexpr int CHUNKS_PER_WARP = BN / 32 / (EPI_WARPS / 4);
+                                                uint32_t tmem_base, int q, int cg, int lane) {
+  constexpr int NC = BN / 32;
   const int num_work = s.m_tiles * s.n_tiles * s.splits;
   int acc = 0;
   uint32_t acc_phase = 0;
@@ -349,13 +350,18 @@ __device__ __forceinline__ void epilogue_direct(const GemmShape& s, const GemmEp
     const int row = m0 + q * 32 + lane;
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
+    if (cg >= NC) {
+      __syncwarp();
+      tc_fence_before();
+      if (lane == 0) tempty_arrive(tc, acc);
+    }
 #pragma unroll 1
-    for (int c = half * CHUNKS_PER_WARP; c < (half + 1) * CHUNKS_PER_WARP; ++c) {
+    for (int c = cg; c < NC; c += 4) {
       uint32_t r[32];
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
       tmem_ld_wait();
-      if (c == (half + 1) * CHUNKS_PER_WARP - 1) {
+      if (c + 4 >= NC) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) tempty_arrive(tc, acc);
@@ -411,7 +417,7 @@ __device__ __forceinline__ void epilogue_direct(const GemmShape& s, const GemmEp
 }
 
 template <int BN, bool A_MN, bool B_MN, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)  // 18 warps are allocated as 20: 96 registers each
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c,
@@ -433,8 +439,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* tfull_bar = empty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;  // [EPI_WARPS][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * EPI_WARPS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -445,6 +450,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc.tile_rows = PAIR ? 256 : BLOCK_M;
   tc.row_off = PAIR ? static_cast<int>(rank) * BLOCK_M : 0;
   tc.tempty_addr = PAIR ? mapa_u32(smem_u32(tempty_bar), 0) : smem_u32(tempty_bar);
+  tc.pair = PAIR;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -461,7 +467,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
-    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -491,7 +496,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int m0 = m_blk * tc.tile_rows + tc.row_off;
         const int n0 = n_blk * BN + (PAIR ? static_cast<int>(rank) * B_ROWS : 0);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_parked(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_TILE_BYTES;
           const int k0 = kb * BLOCK_K;
@@ -545,11 +550,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int sp = w / (s.n_tiles * s.m_tiles);
         const int kb0 = sp * s.kblocks_per_split;
         const int kb1 = min(kb0 + s.kblocks_per_split, s.kblocks_total);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        mbar_wait_parked(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_parked(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t b_base = a_base + A_TILE_BYTES;
@@ -579,32 +584,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else {
     // ------------------------------ epilogue ------------------------------
-    const int q = warp & 3;            // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns it drains
-    uint8_t* stg = staging + (warp - 2) * 2 * STG_BUF_BYTES;
-    uint64_t* abar = aux_bar + (warp - 2) * 2;
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int cg = (warp - 2) >> 2;  // its 32-column chunks: cg, cg + 4, ...
+    uint8_t* stg = staging + (warp - 2) * STG_BUF_BYTES;
     if (!e.tma_out) {
-      epilogue_direct<BN>(s, e, tfull_bar, tc, tmem_base, q, half, lane);
+      epilogue_direct<BN>(s, e, tfull_bar, tc, tmem_base, q, cg, lane);
     } else if (e.mode == VITSSL_EPI_BIAS_GELU) {
-      epilogue_staged<BN, VITSSL_EPI_BIAS_GELU, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                       tc, tmem_base, q, half, lane);
+      epilogue_staged<BN, VITSSL_EPI_BIAS_GELU, false>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q,
+                                                       cg, lane);
     } else if (e.mode == VITSSL_EPI_DGELU) {
-      epilogue_staged<BN, VITSSL_EPI_DGELU, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                   tc, tmem_base, q, half, lane);
+      epilogue_staged<BN, VITSSL_EPI_DGELU, false>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q, cg,
+                                                   lane);
     } else if (e.mode == VITSSL_EPI_BIAS) {
       if (e.out_fp32)
-        epilogue_staged<BN, VITSSL_EPI_BIAS, true>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                   tc, tmem_base, q, half, lane);
+        epilogue_staged<BN, VITSSL_EPI_BIAS, true>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q, cg,
+                                                   lane);
       else
-        epilogue_staged<BN, VITSSL_EPI_BIAS, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                    tc, tmem_base, q, half, lane);
+        epilogue_staged<BN, VITSSL_EPI_BIAS, false>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q, cg,
+                                                    lane);
     } else {
       if (e.out_fp32)
-        epilogue_staged<BN, VITSSL_EPI_NONE, true>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                   tc, tmem_base, q, half, lane);
+        epilogue_staged<BN, VITSSL_EPI_NONE, true>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q, cg,
+                                                   lane);
       else
-        epilogue_staged<BN, VITSSL_EPI_NONE, false>(&tmap_c, &tmap_aux, s, e, stg, abar, tfull_bar,
-                                                    tc, tmem_base, q, half, lane);
+        epilogue_staged<BN, VITSSL_EPI_NONE, false>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q, cg,
+                                                    lane);
     }
   }
 
@@ -786,7 +790,7 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   GemmEpi e{};
   e.c = C; e.ldc = ldc; e.bias = bias; e.aux = reinterpret_cast<__nv_bfloat16*>(aux);
   e.ld_aux = ld_aux; e.alpha = alpha; e.mode = epilogue; e.out_fp32 = out_fp32;
-  e.drop_thresh16 = static_cast<uint32_t>(dropout_p * 65536.0f);
+  e.drop_th2 = static_cast<uint32_t>(dropout_p * 32768.0f) * 0x10001u;
   e.drop_scale = 1.0f / (1.0f - dropout_p);
   e.seed = philox_seed; e.offset = philox_offset;
 
