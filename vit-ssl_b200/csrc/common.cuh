@@ -99,6 +99,38 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint
   return make_uint4(c0, c1, c2, c3);
 }
 constexpr int DROPOUT_PHILOX_ROUNDS = 7;
+// Same generator with the round keys precomputed on the host: as kernel parameters they become
+// constant-bank operands of the round's 3-input XOR, so a round is 2 IMAD.WIDE + 2 LOP3 and no
+// key arithmetic (the in-kernel schedule costs two more ALU instructions per round and draw).
+struct PhiloxKeys7 {
+  uint32_t k[2 * DROPOUT_PHILOX_ROUNDS];  // (k0, k1) of round r at [2r], [2r+1]
+  uint32_t c2, c3;                        // offset words
+};
+inline PhiloxKeys7 make_philox_keys7(uint64_t seed, uint64_t offset) {
+  PhiloxKeys7 pk;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  for (int r = 0; r < DROPOUT_PHILOX_ROUNDS; ++r) {
+    pk.k[2 * r] = k0; pk.k[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  pk.c2 = static_cast<uint32_t>(offset); pk.c3 = static_cast<uint32_t>(offset >> 32);
+  return pk;
+}
+__device__ __forceinline__ uint4 philox4x32_7_keyed(const PhiloxKeys7& pk, uint64_t index) {
+  uint32_t c0 = static_cast<uint32_t>(index), c1 = static_cast<uint32_t>(index >> 32);
+  uint32_t c2 = pk.c2, c3 = pk.c3;
+#pragma unroll
+  for (int r = 0; r < DROPOUT_PHILOX_ROUNDS; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(0xD2511F53u));
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(0xCD9E8D57u));
+    const uint32_t n0 = hi1 ^ c1 ^ pk.k[2 * r], n2 = hi0 ^ c3 ^ pk.k[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
 // Dropout of element e: the 16-bit lanes of one Philox draw cover 8 consecutive elements
 // (draw index = e / 8, lane = e % 8 counted from the low half of .x); keep iff u16 >= thresh16
 // (thresh16 = p * 65536). Both forms below implement exactly this rule.
@@ -193,6 +225,30 @@ __device__ __forceinline__ f32x2 normal_cdf2(float x0, float x1) {
   q = ffma2(s, q, pk2(-6.636010855e-02f, -6.636010855e-02f));
   q = ffma2(s, q, pk2(3.989073634e-01f, 3.989073634e-01f));
   return ffma2(t, q, pk2(0.5f, 0.5f));
+}
+
+// Same function with one clamp per value instead of two: the polynomial argument is
+// s = min(x^2, 4.2^2) and the final multiply-add uses the unclamped x with .sat, which pins the
+// result to [0, 1]; past |x| = 4.2 the line 0.5 + x Q(4.2^2) leaves [0, 1] within 1.3e-5 of the
+// true tail. (min/max run on the half-rate ALU pipe, which bounds the GELU epilogues.)
+__device__ __forceinline__ f32x2 normal_cdf2_sat(float x0, float x1) {
+  const f32x2 x = pk2(x0, x1);
+  float s0, s1;
+  upk2(fmul2(x, x), s0, s1);
+  const f32x2 s = pk2(fminf(s0, 17.64f), fminf(s1, 17.64f));
+  f32x2 q = ffma2(s, pk2(5.994787999e-11f, 5.994787999e-11f), pk2(-5.630807376e-09f, -5.630807376e-09f));
+  q = ffma2(s, q, pk2(2.342876257e-07f, 2.342876257e-07f));
+  q = ffma2(s, q, pk2(-5.759411124e-06f, -5.759411124e-06f));
+  q = ffma2(s, q, pk2(9.456112457e-05f, 9.456112457e-05f));
+  q = ffma2(s, q, pk2(-1.114074141e-03f, -1.114074141e-03f));
+  q = ffma2(s, q, pk2(9.829915129e-03f, 9.829915129e-03f));
+  q = ffma2(s, q, pk2(-6.636010855e-02f, -6.636010855e-02f));
+  q = ffma2(s, q, pk2(3.989073634e-01f, 3.989073634e-01f));
+  float q0, q1, r0, r1;
+  upk2(q, q0, q1);
+  asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(r0) : "f"(x0), "f"(q0));
+  asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(r1) : "f"(x1), "f"(q1));
+  return pk2(r0, r1);
 }
 
 // ----------------------------------------------------------------------------------

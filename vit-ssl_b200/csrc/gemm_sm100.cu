@@ -56,7 +56,7 @@ struct GemmEpi {
   int tma_out;   // 1: epilogue goes through staging + TMA store (tmap_c / tmap_aux valid)
   uint32_t drop_th2;  // (p * 32768) * 0x10001, 0 = no dropout (common.cuh: dropout_lane_mask2)
   float drop_scale;
-  unsigned long long seed, offset;
+  PhiloxKeys7 keys;  // dropout generator state: (seed, offset) expanded to round keys on the host
 };
 
 // PAIR = true: two CTAs of a cluster share one 256 x BN tile (tcgen05 cta_group::2): each CTA
@@ -167,7 +167,7 @@ __device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint
     for (int g = 0; g < 4; ++g) {
       uint32_t keep[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
       if (drop) {
-        const uint4 r = philox4x32<DROPOUT_PHILOX_ROUNDS>(e.seed, e.offset, g8 + g);
+        const uint4 r = philox4x32_7_keyed(e.keys, g8 + g);
         keep[0] = dropout_lane_mask2(r.x, e.drop_th2);
         keep[1] = dropout_lane_mask2(r.y, e.drop_th2);
         keep[2] = dropout_lane_mask2(r.z, e.drop_th2);
@@ -185,7 +185,7 @@ __device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint
           u[i >> 1] = up;
           const float u0 = bf16_lo(up), u1 = bf16_hi(up);
           float h0, h1;
-          upk2(fmul2(fmul2(pk2(u0, u1), scv), normal_cdf2(u0, u1)), h0, h1);
+          upk2(fmul2(fmul2(pk2(u0, u1), scv), normal_cdf2_sat(u0, u1)), h0, h1);
           c[i >> 1] = pack_bf16(h0, h1) & keep[j >> 1];
         } else {
           const uint32_t up = u[i >> 1];
@@ -196,7 +196,7 @@ __device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint
           upk2(fmul2(fmul2(uu, uu), pk2(-0.72134752044448170f, -0.72134752044448170f)), a0, a1);
           const f32x2 pdf = pk2(ex2_approx(a0), ex2_approx(a1));
           const f32x2 upd = fmul2(fmul2(uu, pk2(0.3989422804014327f, 0.3989422804014327f)), pdf);
-          const f32x2 gp = fadd2(upd, normal_cdf2(u0, u1));  // Phi + u phi
+          const f32x2 gp = fadd2(upd, normal_cdf2_sat(u0, u1));  // Phi + u phi
           float d0, d1;
           upk2(fmul2(fmul2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), scv), gp), d0, d1);
           c[i >> 1] = pack_bf16(d0, d1) & keep[j >> 1];
@@ -792,7 +792,7 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   e.ld_aux = ld_aux; e.alpha = alpha; e.mode = epilogue; e.out_fp32 = out_fp32;
   e.drop_th2 = static_cast<uint32_t>(dropout_p * 32768.0f) * 0x10001u;
   e.drop_scale = 1.0f / (1.0f - dropout_p);
-  e.seed = philox_seed; e.offset = philox_offset;
+  e.keys = make_philox_keys7(philox_seed, philox_offset);
 
   // TMA needs 16-byte aligned bases and row pitches
   const bool tma_ok = (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
