@@ -354,6 +354,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
       "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA reduction: global[tile] += shared tile (fp32 add performed at L2 on whole sectors), same
+// bulk-group completion as a store. Split-K partial sums use it instead of per-element red.add.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

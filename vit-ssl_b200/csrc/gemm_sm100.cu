@@ -322,7 +322,8 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(tmap_c, stg, nb, row0);
+        if (OUT_F32 && e.atomic) tma_reduce_add_2d(tmap_c, stg, nb, row0);  // split-K partial sum
+        else tma_store_2d(tmap_c, stg, nb, row0);
         if constexpr (MODE == VITSSL_EPI_BIAS_GELU) tma_store_2d(tmap_aux, stg + 2048, nb, row0);
         tma_store_commit();
       }
@@ -849,7 +850,7 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   s.splits = (s.kblocks_total + s.kblocks_per_split - 1) / s.kblocks_per_split;
   e.atomic = s.splits > 1 ? 1 : 0;
   e.vec_ok = out_ok ? 1 : 0;
-  e.tma_out = (out_ok && !e.atomic) ? 1 : 0;
+  e.tma_out = out_ok ? 1 : 0;  // split-K partials go through the same staging tiles as a TMA reduce-add
   if (e.atomic) {
     cudaError_t err = cudaMemset2DAsync(C, ldc * 4, 0, N * 4, M, stream);
     if (err != cudaSuccess) {
