@@ -68,6 +68,33 @@ def test_attention_cross_lengths_tcgen05():
     assert (out.double().cpu() - ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("B,Sq,Sk,H", [(60, 196, 196, 6), (200, 37, 37, 3), (160, 70, 200, 2), (160, 200, 70, 2),
+                                        (155, 128, 128, 1), (33, 256, 256, 5)])
+def test_attention_bwd_persistent_many_items(B, Sq, Sk, H):
+    """More (batch, head) items than SMs: every CTA of the persistent backward kernel walks several
+    items, so tile slots are recycled across items (1x1, 1x2, 2x1 and 2x2 tilings, cross lengths)."""
+    ops = _ops()
+    D = H * 64
+    g = torch.Generator().manual_seed(B + Sq + 7 * Sk)
+    q = torch.randn(B, Sq, D, generator=g).to(torch.bfloat16)
+    k = torch.randn(B, Sk, D, generator=g).to(torch.bfloat16)
+    v = torch.randn(B, Sk, D, generator=g).to(torch.bfloat16)
+    d_out = torch.randn(B, Sq, D, generator=g).to(torch.bfloat16)
+    qh, kh, vh = [t.double().reshape(B, -1, H, 64).transpose(1, 2).requires_grad_(True) for t in (q, k, v)]
+    ref, _ = vit_ref.scaled_dot_product_attention(qh, kh, vh)
+    (ref.transpose(1, 2).reshape(B, Sq, D) * d_out.double()).sum().backward()
+    qc, kc, vc = q.cuda(), k.cuda(), v.cuda()
+    out, lse = ops.attention_fwd(qc, kc, vc, H, 0.125)
+    dq, dk, dv = torch.empty_like(qc), torch.empty_like(kc), torch.empty_like(vc)
+    for rep in range(2):  # twice: the second launch must not depend on leftover state
+        dq.fill_(7.0); dk.fill_(7.0); dv.fill_(7.0)
+        ops.attention_bwd(qc, kc, vc, out, d_out.cuda(), lse, H, 0.125, dq, dk, dv)
+        for name, got, r in (("dq", dq, qh.grad), ("dk", dk, kh.grad), ("dv", dv, vh.grad)):
+            r = r.transpose(1, 2).reshape(B, -1, D)
+            e = (got.double().cpu() - r).abs().max().item()
+            assert e < 3e-2 * max(1e-3, r.abs().max().item()), (name, rep, e, r.abs().max().item())
+
+
 @pytest.mark.parametrize("B,H,Sq,Sk,d", [(4, 1, 10, 10, 10), (4, 8, 10, 12, 8), (2, 6, 300, 300, 64), (3, 4, 17, 17, 32)])
 def test_attention_generic_fwd_bwd(B, H, Sq, Sk, d):
     ops = _ops()

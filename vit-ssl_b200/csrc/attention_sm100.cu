@@ -269,16 +269,44 @@ struct AttnBwdParams {
 };
 
 constexpr int BWD_MATH_WARPS = 16;  // 4 per TMEM lane quadrant, 32 of the 128 key columns each
-constexpr int BWD_THREADS = 32 * BWD_MATH_WARPS + 32;
-constexpr int BWD_SMEM_Q = 0;          // 2 x 16 KB
-constexpr int BWD_SMEM_DO = 32768;     // 2 x 16 KB
-constexpr int BWD_SMEM_K = 65536;      // 2 x 16 KB
-constexpr int BWD_SMEM_VV = 98304;     // 2 x 16 KB
-constexpr int BWD_SMEM_P = 131072;     // 2 key blocks x 16 KB
-constexpr int BWD_SMEM_DS = 163840;    // 2 key blocks x 16 KB
-constexpr int BWD_SMEM_BAR = 196608;
-constexpr int BWD_SMEM_BYTES = BWD_SMEM_BAR + 128 + 1024;
+constexpr int BWD_WARP_MMA = BWD_MATH_WARPS;      // single-thread tcgen05 issuer
+constexpr int BWD_WARP_TMA = BWD_MATH_WARPS + 1;  // single-thread TMA producer
+constexpr int BWD_THREADS = 32 * (BWD_MATH_WARPS + 2);
+constexpr int BWD_TILE = 16384;  // one 128-row x 64-column bf16 tile (128-byte swizzled rows)
+constexpr int BWD_SMEM_Q = 0 * BWD_TILE;    // 2 slots each: Q, dO, O (query tiles), K, V (key tiles)
+constexpr int BWD_SMEM_DO = 2 * BWD_TILE;
+constexpr int BWD_SMEM_O = 4 * BWD_TILE;
+constexpr int BWD_SMEM_K = 6 * BWD_TILE;
+constexpr int BWD_SMEM_VV = 8 * BWD_TILE;
+constexpr int BWD_SMEM_P = 10 * BWD_TILE;   // P and dS of the current iteration: 2 key blocks x 16 KB each
+constexpr int BWD_SMEM_DS = 12 * BWD_TILE;
+constexpr int BWD_SMEM_BAR = 14 * BWD_TILE;
+constexpr int BWD_SMEM_BYTES = BWD_SMEM_BAR + 256 + 1024;
 
+// 16-byte shared-memory accesses with the state space spelled out (the generic-address forms
+// cost an address-space check per access)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Persistent: one CTA per SM loops over (batch, head) items. Per item the (key tile j, query tile
+// i) iterations run j-outer as before, but the three roles are decoupled so that nothing on the
+// critical path waits for a round trip:
+//   TMA warp  : refills a tile slot as soon as the last MMA that reads it has retired (per-slot
+//               "free" barriers fed by tcgen05.commit), so the next item's Q/dO/O/K/V arrive while
+//               the current item is still computing;
+//   MMA warp  : issues S = Q K^T and dP = dO V^T of iteration g+1 as soon as the math warps hold
+//               S/dP of iteration g in registers (bar_sdp_read), i.e. underneath their exp math,
+//               then dV/dK/dQ of iteration g when P/dS are staged;
+//   math warps: recompute P from the saved LSE, dS = P (dP - delta), stage both as bf16 MMA
+//               operands, and drain dV/dK (per key tile) and dQ (per item) from TMEM.
+// With a single 128x128 tile per item (S <= 128, the DINO local crops) the items alternate
+// between the two tile slots, so loads are double-buffered there too.
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -287,26 +315,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BWD_SMEM_BAR);
-  uint64_t* bar_load = bar + 0;
-  uint64_t* bar_sdp_full = bar + 1;
-  uint64_t* bar_pds_ready = bar + 2;
-  uint64_t* bar_pds_free = bar + 3;
-  uint64_t* bar_dkv_free = bar + 4;
-  uint64_t* bar_sdp_read = bar + 5;  // S / dP of the current iteration are in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 6);
+  uint64_t* bar_ldq = bar + 0;       // [2] Q, dO, O of a query-tile slot landed
+  uint64_t* bar_ldkv = bar + 2;      // [2] K, V of a key-tile slot landed
+  uint64_t* bar_freeq = bar + 4;     // [2] last MMA reading the slot retired
+  uint64_t* bar_freekv = bar + 6;    // [2]
+  uint64_t* bar_sdp_full = bar + 8;  // S / dP of an iteration are in TMEM
+  uint64_t* bar_sdp_read = bar + 9;  // ... and now in the math warps' registers
+  uint64_t* bar_pds_ready = bar + 10;  // P / dS staged in shared memory
+  uint64_t* bar_pds_free = bar + 11;   // dV / dK / dQ MMAs of an iteration retired
+  uint64_t* bar_dkv_free = bar + 12;   // dV / dK accumulators drained
+  uint64_t* bar_dq_free = bar + 13;    // dQ accumulators drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int nq = (p.Sq + 127) / 128, nk = (p.Sk + 127) / 128;  // each <= 2
+  const int nq = (p.Sq + 127) >> 7, nk = (p.Sk + 127) >> 7;  // each 1 or 2
   const int nit = nq * nk;
+  const bool alt = nit == 1;  // single-tile items alternate between the two slots
+  const int items = p.B * p.H;
+  // iteration it -> (key tile j, query tile i), j outer
+  auto it_j = [&](int it) { return nq == 2 ? it >> 1 : it; };
+  auto it_i = [&](int it) { return nq == 2 ? it & 1 : 0; };
 
-  if (warp == BWD_MATH_WARPS) {
+  if (warp == BWD_WARP_TMA) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k);
       tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_o);
-      mbar_init(bar_load, 1); mbar_init(bar_sdp_full, 1); mbar_init(bar_pds_ready, BWD_MATH_WARPS);
-      mbar_init(bar_pds_free, 1); mbar_init(bar_dkv_free, BWD_MATH_WARPS);
-      mbar_init(bar_sdp_read, BWD_MATH_WARPS);
+      for (int i = 0; i < 8; ++i) mbar_init(bar + i, 1);
+      mbar_init(bar_sdp_full, 1); mbar_init(bar_sdp_read, BWD_MATH_WARPS);
+      mbar_init(bar_pds_ready, BWD_MATH_WARPS); mbar_init(bar_pds_free, 1);
+      mbar_init(bar_dkv_free, BWD_MATH_WARPS); mbar_init(bar_dq_free, BWD_MATH_WARPS);
       fence_barrier_init();
     }
     __syncwarp();
@@ -318,30 +355,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
 
-  if (warp == BWD_MATH_WARPS) {
+  if (warp == BWD_WARP_TMA) {
+    // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      mbar_expect_tx(bar_load, static_cast<uint32_t>(3 * nq + 2 * nk) * 16384u);
-      for (int i = 0; i < nq; ++i) {
-        tma_load_3d(smem + BWD_SMEM_Q + i * 16384, &tmap_q, bar_load, h * 64, i * 128, b);
-        tma_load_3d(smem + BWD_SMEM_DO + i * 16384, &tmap_do, bar_load, h * 64, i * 128, b);
-        // O only feeds delta = rowsum(O * dO); it borrows the P region, which is idle until then
-        tma_load_3d(smem + BWD_SMEM_P + i * 16384, &tmap_o, bar_load, h * 64, i * 128, b);
+      int n = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+        const int h = item % p.H, b = item / p.H;
+        const int u = alt ? n >> 1 : n;  // how often this item's slots have been used before
+        auto load_kv = [&](int j) {
+          const int sl = alt ? (n & 1) : j;
+          if (u > 0) mbar_wait_parked(&bar_freekv[sl], (u - 1) & 1);
+          mbar_expect_tx(&bar_ldkv[sl], 2 * BWD_TILE);
+          tma_load_3d(smem + BWD_SMEM_K + sl * BWD_TILE, &tmap_k, &bar_ldkv[sl], h * 64, j * 128, b);
+          tma_load_3d(smem + BWD_SMEM_VV + sl * BWD_TILE, &tmap_v, &bar_ldkv[sl], h * 64, j * 128, b);
+        };
+        auto load_q = [&](int i) {
+          const int sl = alt ? (n & 1) : i;
+          if (u > 0) mbar_wait_parked(&bar_freeq[sl], (u - 1) & 1);
+          mbar_expect_tx(&bar_ldq[sl], 3 * BWD_TILE);
+          tma_load_3d(smem + BWD_SMEM_Q + sl * BWD_TILE, &tmap_q, &bar_ldq[sl], h * 64, i * 128, b);
+          tma_load_3d(smem + BWD_SMEM_DO + sl * BWD_TILE, &tmap_do, &bar_ldq[sl], h * 64, i * 128, b);
+          tma_load_3d(smem + BWD_SMEM_O + sl * BWD_TILE, &tmap_o, &bar_ldq[sl], h * 64, i * 128, b);
+        };
+        // in the order the slots are released by the previous item and first needed by this one
+        load_kv(0);
+        load_q(0);
+        if (nq > 1) load_q(1);
+        if (nk > 1) load_kv(1);
       }
-      for (int j = 0; j < nk; ++j) {
-        tma_load_3d(smem + BWD_SMEM_K + j * 16384, &tmap_k, bar_load, h * 64, j * 128, b);
-        tma_load_3d(smem + BWD_SMEM_VV + j * 16384, &tmap_v, bar_load, h * 64, j * 128, b);
-      }
+    }
+  } else if (warp == BWD_WARP_MMA) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
       constexpr uint32_t idesc_sdp = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_dkv = umma_idesc_bf16(128, 64, true, true);
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, false, true);
       const uint32_t sq = smem_u32(smem + BWD_SMEM_Q), sdo = smem_u32(smem + BWD_SMEM_DO);
       const uint32_t sk = smem_u32(smem + BWD_SMEM_K), sv = smem_u32(smem + BWD_SMEM_VV);
       const uint32_t sp = smem_u32(smem + BWD_SMEM_P), sds = smem_u32(smem + BWD_SMEM_DS);
-
-      auto issue_sdp = [&](int it) {
-        const int j = it / nq, i = it % nq;
-        const uint32_t qi = sq + i * 16384, doi = sdo + i * 16384;
-        const uint32_t kj = sk + j * 16384, vj = sv + j * 16384;
+      // S / dP of iteration `it` of the CTA's n-th item; waits for tiles this iteration uses first
+      auto issue_sdp = [&](int n, int it) {
+        const int j = it_j(it), i = it_i(it);
+        const int u = alt ? n >> 1 : n;
+        const int slq = alt ? (n & 1) : i, slk = alt ? (n & 1) : j;
+        if (j == 0) mbar_wait(&bar_ldq[slq], u & 1);
+        if (i == 0) mbar_wait(&bar_ldkv[slk], u & 1);
+        tc_fence_after();
+        const uint32_t qi = sq + slq * BWD_TILE, doi = sdo + slq * BWD_TILE;
+        const uint32_t kj = sk + slk * BWD_TILE, vj = sv + slk * BWD_TILE;
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // S = Q_i K_j^T
           umma_bf16_ss(tmem + COL_S, umma_desc_sw128(qi + k * 32, 16, 1024),
@@ -352,149 +413,81 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                        umma_desc_sw128(vj + k * 32, 16, 1024), idesc_sdp, k > 0);
         umma_commit(bar_sdp_full);
       };
-
-      mbar_wait(bar_load, 0);
-      tc_fence_after();
-      issue_sdp(0);
-      for (int it = 0; it < nit; ++it) {
-        const int j = it / nq, i = it % nq;
-        mbar_wait(bar_pds_ready, it & 1);
-        tc_fence_after();
-        if (it + 1 < nit) issue_sdp(it + 1);
-        if (i == 0 && j > 0) {
-          mbar_wait(bar_dkv_free, (j - 1) & 1);
+      // the next item's first S / dP may be issued under the current item's last iteration only
+      // if its tiles are released by earlier iterations (true for the 2 x 2 tiling)
+      const bool early_cross = nq == 2 && nk == 2;
+      uint32_t g = 0, kt = 0;  // iterations / key tiles processed by this CTA so far
+      int n = 0;
+      if (blockIdx.x < items) issue_sdp(0, 0);
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+        const bool more_items = item + static_cast<int>(gridDim.x) < items;
+        for (int it = 0; it < nit; ++it, ++g) {
+          const int j = it_j(it), i = it_i(it);
+          const bool in_item = it + 1 < nit;
+          const bool have_next = in_item || more_items;
+          const bool early = in_item || early_cross;
+          if (have_next && early) {
+            mbar_wait(bar_sdp_read, g & 1);
+            tc_fence_after();
+            if (in_item) issue_sdp(n, it + 1); else issue_sdp(n + 1, 0);
+          }
+          mbar_wait(bar_pds_ready, g & 1);
+          if (i == 0 && kt > 0) mbar_wait(bar_dkv_free, (kt - 1) & 1);  // previous key tile drained
+          if (it == 0 && n > 0) mbar_wait(bar_dq_free, (n - 1) & 1);     // previous item's dQ drained
           tc_fence_after();
+          const int slq = alt ? (n & 1) : i, slk = alt ? (n & 1) : j;
+          const uint32_t qi = sq + slq * BWD_TILE, doi = sdo + slq * BWD_TILE, kj = sk + slk * BWD_TILE;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dV_j += P^T dO_i   (reduction over the 128 query rows)
+            umma_bf16_ss(tmem + COL_DV, umma_desc_sw128(sp + ks * 2048, 16384, 1024),
+                         umma_desc_sw128(doi + ks * 2048, 8192, 1024), idesc_dkv, (i > 0 || ks > 0));
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dK_j += dS^T Q_i
+            umma_bf16_ss(tmem + COL_DK, umma_desc_sw128(sds + ks * 2048, 16384, 1024),
+                         umma_desc_sw128(qi + ks * 2048, 8192, 1024), idesc_dkv, (i > 0 || ks > 0));
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dQ_i += dS K_j     (reduction over the 128 keys)
+            umma_bf16_ss(tmem + COL_DQ + i * 64,
+                         umma_desc_sw128(sds + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                         umma_desc_sw128(kj + ks * 2048, 8192, 1024), idesc_dq, (j > 0 || ks > 0));
+          umma_commit(bar_pds_free);
+          if (j == nk - 1) umma_commit(&bar_freeq[slq]);   // last reader of Q_i / dO_i
+          if (i == nq - 1) umma_commit(&bar_freekv[slk]);  // last reader of K_j / V_j
+          if (have_next && !early) issue_sdp(n + 1, 0);    // (S / dP were read before P / dS were staged)
+          if (i == nq - 1) ++kt;
         }
-        const uint32_t qi = sq + i * 16384, doi = sdo + i * 16384, kj = sk + j * 16384;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)  // dV_j += P^T dO_i   (reduction over the 128 query rows)
-          umma_bf16_ss(tmem + COL_DV, umma_desc_sw128(sp + ks * 2048, 16384, 1024),
-                       umma_desc_sw128(doi + ks * 2048, 8192, 1024), idesc_dkv, (i > 0 || ks > 0));
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)  // dK_j += dS^T Q_i
-          umma_bf16_ss(tmem + COL_DK, umma_desc_sw128(sds + ks * 2048, 16384, 1024),
-                       umma_desc_sw128(qi + ks * 2048, 8192, 1024), idesc_dkv, (i > 0 || ks > 0));
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)  // dQ_i += dS K_j     (reduction over the 128 keys)
-          umma_bf16_ss(tmem + COL_DQ + i * 64,
-                       umma_desc_sw128(sds + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                       umma_desc_sw128(kj + ks * 2048, 8192, 1024), idesc_dq, (j > 0 || ks > 0));
-        umma_commit(bar_pds_free);
       }
     }
   } else {
     // 512 math threads: row r = TMEM lane, `cq` selects 32 of the 128 key columns of the tile
-    const int t = threadIdx.x;
-    const int r = t & 127, cq = t >> 7;
+    const int r = threadIdx.x & 127, cq = threadIdx.x >> 7;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const float sl2 = p.scale * kLog2e;
-    float delta0 = 0.f, delta1 = 0.f, nlse0 = 0.f, nlse1 = 0.f;
-    bool qvalid0 = false, qvalid1 = false;
-    mbar_wait(bar_load, 0);
-    // delta_i = sum_d O[i, d] * dO[i, d] from the TMA-staged (128B-swizzled) tiles in shared memory
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int qrow = i * 128 + r;
-      const bool valid = i < nq && qrow < p.Sq;
-      if (i == 0) qvalid0 = valid; else qvalid1 = valid;
-      if (valid) {
-        const uint8_t* so = smem + BWD_SMEM_P + i * 16384 + r * 128;
-        const uint8_t* sd = smem + BWD_SMEM_DO + i * 16384 + r * 128;
-        f32x2 acc2 = pk2(0.f, 0.f);
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const int sw = (v ^ (r & 7)) << 4;
-          const uint4 a = *reinterpret_cast<const uint4*>(so + sw);
-          const uint4 d = *reinterpret_cast<const uint4*>(sd + sw);
-          acc2 = ffma2(pk2(bf16_lo(a.x), bf16_hi(a.x)), pk2(bf16_lo(d.x), bf16_hi(d.x)), acc2);
-          acc2 = ffma2(pk2(bf16_lo(a.y), bf16_hi(a.y)), pk2(bf16_lo(d.y), bf16_hi(d.y)), acc2);
-          acc2 = ffma2(pk2(bf16_lo(a.z), bf16_hi(a.z)), pk2(bf16_lo(d.z), bf16_hi(d.z)), acc2);
-          acc2 = ffma2(pk2(bf16_lo(a.w), bf16_hi(a.w)), pk2(bf16_lo(d.w), bf16_hi(d.w)), acc2);
-        }
-        float a0, a1;
-        upk2(acc2, a0, a1);
-        const float nl = -p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qrow] * kLog2e;
-        if (i == 0) { delta0 = a0 + a1; nlse0 = nl; } else { delta1 = a0 + a1; nlse1 = nl; }
-      }
-    }
-    // every math thread has read O before anyone overwrites the region with P
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * BWD_MATH_WARPS) : "memory");
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sbar = sbase + BWD_SMEM_BAR;  // barrier k lives at sbar + 8k
     // this thread's 4 x 16-byte chunks (32 keys) inside key block (cq >> 1) of the P / dS tiles
-    uint8_t* sP = smem + BWD_SMEM_P + (cq >> 1) * 16384 + r * 128;
-    uint8_t* sDS = smem + BWD_SMEM_DS + (cq >> 1) * 16384 + r * 128;
+    const uint32_t sP = sbase + BWD_SMEM_P + (cq >> 1) * 16384 + r * 128;
 
-    for (int it = 0; it < nit; ++it) {
-      const int j = it / nq, i = it % nq;
-      mbar_wait(bar_sdp_full, it & 1);
-      tc_fence_after();
-      // invalid query rows recompute p = 2^(-inf) = 0 (their S rows are zero: TMA zero-fills Q)
-      const bool rv = i ? qvalid1 : qvalid0;
-      const float dl = i ? delta1 : delta0, nl = rv ? (i ? nlse1 : nlse0) : -INFINITY;
-      const f32x2 sl2v = pk2(sl2, sl2), nlv = pk2(nl, nl), ndlv = pk2(-dl, -dl);
-      uint32_t pp[2][8], dd[2][8];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {  // two sub-chunks of 16 keys
-        const int key0 = j * 128 + cq * 32 + c * 16;
-        if (key0 < p.Sk) {
-          uint32_t sv[16], dp[16];
-          __syncwarp();
-          tmem_ld_32x16(lane_addr + COL_S + cq * 32 + c * 16, sv);
-          tmem_ld_32x16(lane_addr + COL_DP + cq * 32 + c * 16, dp);
-          tmem_ld_wait();
-          const bool full = key0 + 16 <= p.Sk;
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float a0, a1;
-            upk2(ffma2(pk2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2v, nlv), a0, a1);
-            float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-            if (!full) {
-              p0 = (key0 + e < p.Sk) ? p0 : 0.f;
-              p1 = (key0 + e + 1 < p.Sk) ? p1 : 0.f;
-            }
-            pp[c][e >> 1] = pack_bf16(p0, p1);
-            float d0, d1;  // dS = P * (dP - delta)
-            upk2(fmul2(pk2(p0, p1), fadd2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ndlv)), d0, d1);
-            dd[c][e >> 1] = pack_bf16(d0, d1);
-          }
-        } else {  // key chunk entirely past Sk
-#pragma unroll
-          for (int e = 0; e < 8; ++e) pp[c][e] = dd[c][e] = 0u;
-        }
-      }
-      // everything above overlapped the previous iteration's dV / dK / dQ MMAs; only the stores
-      // need their P / dS operands to have been consumed
-      if (it > 0) mbar_wait(bar_pds_free, (it - 1) & 1);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int chunk = (cq & 1) * 4 + c * 2 + g;
-          const int sw = (chunk ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pp[c][4 * g], pp[c][4 * g + 1], pp[c][4 * g + 2], pp[c][4 * g + 3]);
-          *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dd[c][4 * g], dd[c][4 * g + 1], dd[c][4 * g + 2], dd[c][4 * g + 3]);
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pds_ready);  // one arrival per warp
-
-      if (i == nq - 1) {
-        // key tile j finished: warps 0-7 drain dV_j, warps 8-15 dK_j; 32 of the 64 columns each
-        mbar_wait(bar_pds_free, it & 1);
-        tc_fence_after();
-        const int krow = j * 128 + r;
-        const int sel = cq >> 1, cc = cq & 1;
-        const uint32_t col = (sel == 0 ? COL_DV : COL_DK) + cc * 32;
-        const float mul = sel == 0 ? 1.0f : p.scale;
-        __nv_bfloat16* base = sel == 0 ? p.dv : p.dk;
-        const long long ld = sel == 0 ? p.lddv : p.lddk;
+    // TMEM accumulators -> global: dV_j / dK_j when a key tile is complete (warps 0-7 take dV,
+    // warps 8-15 dK; 32 of the 64 columns each), dQ when the item is complete (thread group cq
+    // takes columns (cq & 1) * 32 .. +32 of query tile cq >> 1). The drains of iteration g run
+    // inside iteration g+1, after its exp math and before its P / dS stores, so waiting for the
+    // MMAs of iteration g costs nothing.
+    auto drain = [&](int item, int j, bool key_tile_done, bool item_done) {
+      const int h = item % p.H, b = item / p.H;
+      const int sel = cq >> 1, cc = cq & 1;
+      if (key_tile_done) {
         uint32_t v[32];
         __syncwarp();
-        tmem_ld_32x32(lane_addr + col, v);
+        tmem_ld_32x32(lane_addr + (sel == 0 ? COL_DV : COL_DK) + cc * 32, v);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_addr(sbar + 8 * 12);  // bar_dkv_free: accumulators are in registers
+        const int krow = j * 128 + r;
         if (krow < p.Sk) {
-          __nv_bfloat16* op = base + (static_cast<long long>(b) * p.Sk + krow) * ld + h * 64 + cc * 32;
+          const float mul = sel == 0 ? 1.0f : p.scale;
+          __nv_bfloat16* op = (sel == 0 ? p.dv : p.dk) +
+                              (static_cast<long long>(b) * p.Sk + krow) * (sel == 0 ? p.lddv : p.lddk) + h * 64 + cc * 32;
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             uint4 o;
@@ -505,22 +498,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             *reinterpret_cast<uint4*>(op + e) = o;
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dkv_free);
       }
-    }
-    // dQ: thread group cq drains columns (cq & 1) * 32 .. +32 of query tile cq >> 1 (all MMAs have
-    // retired: the last bar_pds_free phase was waited on above)
-    {
-      const int tile = cq >> 1, cc = cq & 1;
-      if (tile < nq) {
-        const int qrow = tile * 128 + r;
+      if (item_done) {
         uint32_t v[32];
         __syncwarp();
-        tmem_ld_32x32(lane_addr + COL_DQ + tile * 64 + cc * 32, v);
-        tmem_ld_wait();
-        if (qrow < p.Sq) {
+        if (sel < nq) {
+          tmem_ld_32x32(lane_addr + COL_DQ + sel * 64 + cc * 32, v);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_addr(sbar + 8 * 13);  // bar_dq_free
+        const int qrow = sel * 128 + r;
+        if (sel < nq && qrow < p.Sq) {
           __nv_bfloat16* op = p.dq + (static_cast<long long>(b) * p.Sq + qrow) * p.lddq + h * 64 + cc * 32;
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
@@ -533,11 +523,110 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
+    };
+
+    uint32_t g = 0;
+    int n = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+      float delta0 = 0.f, delta1 = 0.f, nlse0 = -INFINITY, nlse1 = -INFINITY;
+      for (int it = 0; it < nit; ++it, ++g) {
+        const int j = it_j(it), i = it_i(it);
+        if (j == 0) {
+          // first use of query tile i: delta_i = sum_d O[i, d] * dO[i, d] from the staged tiles,
+          // and -lse * log2(e). Invalid query rows keep nlse = -inf, so their p = 2^(-inf) = 0.
+          const int slq = alt ? (n & 1) : i;
+          mbar_wait_parked_addr(sbar + 8 * slq, (alt ? n >> 1 : n) & 1);  // bar_ldq[slq]
+          const int qrow = i * 128 + r;
+          float dl = 0.f, nl = -INFINITY;
+          if (qrow < p.Sq) {
+            const uint32_t so = sbase + BWD_SMEM_O + slq * BWD_TILE + r * 128;
+            const uint32_t sd = sbase + BWD_SMEM_DO + slq * BWD_TILE + r * 128;
+            f32x2 acc2 = pk2(0.f, 0.f);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const int sw = (v ^ (r & 7)) << 4;
+              const uint4 a = lds128(so + sw);
+              const uint4 d = lds128(sd + sw);
+              acc2 = ffma2(pk2(bf16_lo(a.x), bf16_hi(a.x)), pk2(bf16_lo(d.x), bf16_hi(d.x)), acc2);
+              acc2 = ffma2(pk2(bf16_lo(a.y), bf16_hi(a.y)), pk2(bf16_lo(d.y), bf16_hi(d.y)), acc2);
+              acc2 = ffma2(pk2(bf16_lo(a.z), bf16_hi(a.z)), pk2(bf16_lo(d.z), bf16_hi(d.z)), acc2);
+              acc2 = ffma2(pk2(bf16_lo(a.w), bf16_hi(a.w)), pk2(bf16_lo(d.w), bf16_hi(d.w)), acc2);
+            }
+            float a0, a1;
+            upk2(acc2, a0, a1);
+            dl = a0 + a1;
+            nl = -p.lse[(static_cast<long long>(item) * p.Sq) + qrow] * kLog2e;  // lse is [B, H, Sq]
+          }
+          if (i == 0) { delta0 = dl; nlse0 = nl; } else { delta1 = dl; nlse1 = nl; }
+        }
+        mbar_wait_parked_addr(sbar + 8 * 8, g & 1);  // bar_sdp_full
+        tc_fence_after();
+        const float sl2 = p.scale * kLog2e;
+        const float dl = i ? delta1 : delta0, nl = i ? nlse1 : nlse0;
+        const f32x2 sl2v = pk2(sl2, sl2), nlv = pk2(nl, nl), ndlv = pk2(-dl, -dl);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // four sub-chunks of 8 keys = one 16-byte P / dS store each
+          const int key0 = j * 128 + cq * 32 + c * 8;
+          uint32_t sv[8], dp[8], pp[4], dd[4];
+          const bool live = key0 < p.Sk;
+          __syncwarp();
+          if (live) {
+            tmem_ld_32x8(lane_addr + COL_S + cq * 32 + c * 8, sv);
+            tmem_ld_32x8(lane_addr + COL_DP + cq * 32 + c * 8, dp);
+            tmem_ld_wait();
+          }
+          if (c == 3) {  // S / dP of this iteration are in registers: the next S / dP MMAs may overwrite them
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_addr(sbar + 8 * 9);  // bar_sdp_read
+          }
+          if (live) {
+            const bool full = key0 + 8 <= p.Sk;
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              float a0, a1;
+              upk2(ffma2(pk2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2v, nlv), a0, a1);
+              float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+              if (!full) {
+                p0 = (key0 + e < p.Sk) ? p0 : 0.f;
+                p1 = (key0 + e + 1 < p.Sk) ? p1 : 0.f;
+              }
+              pp[e >> 1] = pack_bf16(p0, p1);
+              float d0, d1;  // dS = P * (dP - delta)
+              upk2(fmul2(pk2(p0, p1), fadd2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ndlv)), d0, d1);
+              dd[e >> 1] = pack_bf16(d0, d1);
+            }
+          } else {  // key chunk entirely past Sk
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pp[e] = dd[e] = 0u;
+          }
+          if (c == 0 && g > 0) {
+            // the math above overlapped the previous iteration's dV / dK / dQ MMAs; the stores need
+            // their P / dS operands consumed, and that iteration's finished accumulators are drained
+            mbar_wait_parked_addr(sbar + 8 * 11, (g - 1) & 1);  // bar_pds_free
+            tc_fence_after();
+            if (it == 0) drain(item - static_cast<int>(gridDim.x), nk - 1, true, true);
+            else if (i == 0) drain(item, j - 1, true, false);
+          }
+          const int sw = (((cq & 1) * 4 + c) ^ (r & 7)) << 4;
+          sts128(sP + sw, pp[0], pp[1], pp[2], pp[3]);
+          sts128(sP + (BWD_SMEM_DS - BWD_SMEM_P) + sw, dd[0], dd[1], dd[2], dd[3]);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_addr(sbar + 8 * 10);  // bar_pds_ready: one arrival per warp
+      }
+    }
+    if (g > 0) {  // the CTA's last item
+      mbar_wait_parked_addr(sbar + 8 * 11, (g - 1) & 1);
+      tc_fence_after();
+      drain(blockIdx.x + (n - 1) * static_cast<int>(gridDim.x), nk - 1, true, true);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == BWD_MATH_WARPS) {
+  if (warp == BWD_WARP_TMA) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -746,7 +835,8 @@ extern "C" int vitssl_attention_bwd(const void* q, const void* k, const void* v,
     if (err != cudaSuccess) { set_error("attention_bwd: smem attribute: %s", cudaGetErrorString(err)); return VITSSL_ERR_CUDA; }
     configured = true;
   }
-  dim3 grid((unsigned)H, (unsigned)B);
+  const long long items = (long long)B * H;  // persistent: one CTA per SM walks the (batch, head) items
+  const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
   attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(mq, mk, mv, mdo, mo, p);
   return check_launch("attention_bwd");
 }

@@ -319,6 +319,27 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
     }
   }
 }
+__device__ __forceinline__ void mbar_wait_parked_addr(uint32_t cta_addr, uint32_t parity) {
+  auto try_wait = [&]() {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(cta_addr), "r"(parity), "r"(200000u)
+        : "memory");
+    return ok != 0;
+  };
+  if (try_wait()) return;
+  const long long t0 = clock64();
+  while (!try_wait()) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("vitssl: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t cta_addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cta_addr) : "memory");
 }
@@ -451,6 +472,13 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
