@@ -25,7 +25,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-I", CSRC, "-I", INCLUDE,
-]
+] + os.environ.get("VITSSL_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _digest(paths):

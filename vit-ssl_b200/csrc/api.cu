@@ -90,14 +90,24 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2,
                       uint64_t ld1_bytes, uint64_t ld2_bytes, uint32_t box_inner, uint32_t box_d1,
                       uint32_t box_d2) {
+  return make_tmap_bf16_3d_sw(out, base, inner, d1, d2, ld1_bytes, ld2_bytes, box_inner, box_d1, box_d2, 128);
+}
+
+int make_tmap_bf16_3d_sw(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2,
+                         uint64_t ld1_bytes, uint64_t ld2_bytes, uint32_t box_inner, uint32_t box_d1,
+                         uint32_t box_d2, int swizzle_bytes) {
   auto fn = encode_fn();
+  const CUtensorMapSwizzle swz = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                       : CU_TENSOR_MAP_SWIZZLE_NONE;
   VITSSL_REQUIRE(fn != nullptr, VITSSL_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {inner, d1, d2};
   cuuint64_t strides[2] = {ld1_bytes, ld2_bytes};
   cuuint32_t box[3] = {box_inner, box_d1, box_d2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VITSSL_REQUIRE(r == CUDA_SUCCESS, VITSSL_ERR_CUDA,
                  "cuTensorMapEncodeTiled(3d) failed: %d (dims %llu %llu %llu pitches %llu %llu)",

@@ -268,6 +268,12 @@ struct AttnBwdParams {
   float scale;
 };
 
+#ifdef VITSSL_ATTN_TRACE
+__device__ long long g_attn_trace[8192];
+#define TRACE(slot) do { if (blockIdx.x == 0 && (slot) < 8192) g_attn_trace[(slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
 constexpr int BWD_MATH_WARPS = 16;  // 4 per TMEM lane quadrant, 32 of the 128 key columns each
 constexpr int BWD_WARP_MMA = BWD_MATH_WARPS;      // single-thread tcgen05 issuer
 constexpr int BWD_WARP_TMA = BWD_MATH_WARPS + 1;  // single-thread TMA producer
@@ -310,7 +316,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                const __grid_constant__ CUtensorMap tmap_o, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_dq,
+                const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
+                const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -340,6 +348,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k);
       tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_o);
+      tma_prefetch_desc(&tmap_dq); tma_prefetch_desc(&tmap_dk); tma_prefetch_desc(&tmap_dv);
       for (int i = 0; i < 8; ++i) mbar_init(bar + i, 1);
       mbar_init(bar_sdp_full, 1); mbar_init(bar_sdp_read, BWD_MATH_WARPS);
       mbar_init(bar_pds_ready, BWD_MATH_WARPS); mbar_init(bar_pds_free, 1);
@@ -352,7 +361,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  // The CTA owns the SM's whole tensor memory (512 columns, one CTA per SM), so the allocation
+  // starts at lane 0 / column 0. Treating that as a constant keeps every tcgen05.mma operand of the
+  // issuing thread in uniform registers (a base loaded from shared memory costs a vector->uniform
+  // hand-off sequence per MMA).
+  if (*tmem_slot != 0u) {
+    if (threadIdx.x == 0) printf("vitssl: attention_bwd expects the TMEM allocation at column 0\n");
+    __trap();
+  }
+  constexpr uint32_t tmem = 0;
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
 
   if (warp == BWD_WARP_TMA) {
@@ -390,9 +407,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       constexpr uint32_t idesc_sdp = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_dkv = umma_idesc_bf16(128, 64, true, true);
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, false, true);
-      const uint32_t sq = smem_u32(smem + BWD_SMEM_Q), sdo = smem_u32(smem + BWD_SMEM_DO);
-      const uint32_t sk = smem_u32(smem + BWD_SMEM_K), sv = smem_u32(smem + BWD_SMEM_VV);
-      const uint32_t sp = smem_u32(smem + BWD_SMEM_P), sds = smem_u32(smem + BWD_SMEM_DS);
+      // Descriptor low words (start address >> 4 | leading-byte-offset field) of every operand
+      // tile, computed once; advancing inside a tile adds (bytes >> 4). All forms share the high
+      // word (SBO = 1024, version 1, 128-byte swizzle).
+      constexpr uint32_t LBO_K = (16u >> 4) << 16;        // K-major operand
+      constexpr uint32_t LBO_MN = (8192u >> 4) << 16;     // MN-major, 64-wide groups 8 KB apart
+      constexpr uint32_t LBO_MN2 = (16384u >> 4) << 16;   // MN-major P / dS: key blocks 16 KB apart
+      const uint32_t sb = smem_u32(smem) >> 4;
+      auto lo = [&](int byte_off, uint32_t lbo) { return (sb + (static_cast<uint32_t>(byte_off) >> 4)) | lbo; };
+      auto mma = [&](uint32_t d_col, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool acc) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_col),
+            "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(static_cast<uint32_t>(acc)), "r"(0x40004040u)
+            : "memory");
+      };
       // S / dP of iteration `it` of the CTA's n-th item; waits for tiles this iteration uses first
       auto issue_sdp = [&](int n, int it) {
         const int j = it_j(it), i = it_i(it);
@@ -401,21 +432,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (j == 0) mbar_wait(&bar_ldq[slq], u & 1);
         if (i == 0) mbar_wait(&bar_ldkv[slk], u & 1);
         tc_fence_after();
-        const uint32_t qi = sq + slq * BWD_TILE, doi = sdo + slq * BWD_TILE;
-        const uint32_t kj = sk + slk * BWD_TILE, vj = sv + slk * BWD_TILE;
+        const uint32_t q_k = lo(BWD_SMEM_Q + slq * BWD_TILE, LBO_K), do_k = lo(BWD_SMEM_DO + slq * BWD_TILE, LBO_K);
+        const uint32_t k_k = lo(BWD_SMEM_K + slk * BWD_TILE, LBO_K), v_k = lo(BWD_SMEM_VV + slk * BWD_TILE, LBO_K);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // S = Q_i K_j^T
-          umma_bf16_ss(tmem + COL_S, umma_desc_sw128(qi + k * 32, 16, 1024),
-                       umma_desc_sw128(kj + k * 32, 16, 1024), idesc_sdp, k > 0);
+        for (int k = 0; k < 4; ++k) mma(COL_S, q_k + 2 * k, k_k + 2 * k, idesc_sdp, k > 0);    // S = Q_i K_j^T
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // dP = dO_i V_j^T
-          umma_bf16_ss(tmem + COL_DP, umma_desc_sw128(doi + k * 32, 16, 1024),
-                       umma_desc_sw128(vj + k * 32, 16, 1024), idesc_sdp, k > 0);
+        for (int k = 0; k < 4; ++k) mma(COL_DP, do_k + 2 * k, v_k + 2 * k, idesc_sdp, k > 0);  // dP = dO_i V_j^T
         umma_commit(bar_sdp_full);
       };
       // the next item's first S / dP may be issued under the current item's last iteration only
       // if its tiles are released by earlier iterations (true for the 2 x 2 tiling)
       const bool early_cross = nq == 2 && nk == 2;
+      const uint32_t p_mn = lo(BWD_SMEM_P, LBO_MN2), ds_mn = lo(BWD_SMEM_DS, LBO_MN2), ds_k = lo(BWD_SMEM_DS, LBO_K);
       uint32_t g = 0, kt = 0;  // iterations / key tiles processed by this CTA so far
       int n = 0;
       if (blockIdx.x < items) issue_sdp(0, 0);
@@ -428,29 +456,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const bool early = in_item || early_cross;
           if (have_next && early) {
             mbar_wait(bar_sdp_read, g & 1);
+            TRACE(16 * g + 0);
             tc_fence_after();
             if (in_item) issue_sdp(n, it + 1); else issue_sdp(n + 1, 0);
           }
+          TRACE(16 * g + 1);
           mbar_wait(bar_pds_ready, g & 1);
+          TRACE(16 * g + 2);
           if (i == 0 && kt > 0) mbar_wait(bar_dkv_free, (kt - 1) & 1);  // previous key tile drained
           if (it == 0 && n > 0) mbar_wait(bar_dq_free, (n - 1) & 1);     // previous item's dQ drained
           tc_fence_after();
           const int slq = alt ? (n & 1) : i, slk = alt ? (n & 1) : j;
-          const uint32_t qi = sq + slq * BWD_TILE, doi = sdo + slq * BWD_TILE, kj = sk + slk * BWD_TILE;
+          const uint32_t q_mn = lo(BWD_SMEM_Q + slq * BWD_TILE, LBO_MN), do_mn = lo(BWD_SMEM_DO + slq * BWD_TILE, LBO_MN);
+          const uint32_t k_mn = lo(BWD_SMEM_K + slk * BWD_TILE, LBO_MN);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // dV_j += P^T dO_i   (reduction over the 128 query rows)
-            umma_bf16_ss(tmem + COL_DV, umma_desc_sw128(sp + ks * 2048, 16384, 1024),
-                         umma_desc_sw128(doi + ks * 2048, 8192, 1024), idesc_dkv, (i > 0 || ks > 0));
+            mma(COL_DV, p_mn + 128 * ks, do_mn + 128 * ks, idesc_dkv, i > 0 || ks > 0);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // dK_j += dS^T Q_i
-            umma_bf16_ss(tmem + COL_DK, umma_desc_sw128(sds + ks * 2048, 16384, 1024),
-                         umma_desc_sw128(qi + ks * 2048, 8192, 1024), idesc_dkv, (i > 0 || ks > 0));
+            mma(COL_DK, ds_mn + 128 * ks, q_mn + 128 * ks, idesc_dkv, i > 0 || ks > 0);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // dQ_i += dS K_j     (reduction over the 128 keys)
-            umma_bf16_ss(tmem + COL_DQ + i * 64,
-                         umma_desc_sw128(sds + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                         umma_desc_sw128(kj + ks * 2048, 8192, 1024), idesc_dq, (j > 0 || ks > 0));
+            mma(COL_DQ + i * 64, ds_k + (ks >> 2) * 1024 + (ks & 3) * 2, k_mn + 128 * ks, idesc_dq, j > 0 || ks > 0);
           umma_commit(bar_pds_free);
+          TRACE(16 * g + 3);
           if (j == nk - 1) umma_commit(&bar_freeq[slq]);   // last reader of Q_i / dO_i
           if (i == nq - 1) umma_commit(&bar_freekv[slk]);  // last reader of K_j / V_j
           if (have_next && !early) issue_sdp(n + 1, 0);    // (S / dP were read before P / dS were staged)
@@ -461,21 +490,43 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   } else {
     // 512 math threads: row r = TMEM lane, `cq` selects 32 of the 128 key columns of the tile
     const int r = threadIdx.x & 127, cq = threadIdx.x >> 7;
-    const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sbar = sbase + BWD_SMEM_BAR;  // barrier k lives at sbar + 8k
     // this thread's 4 x 16-byte chunks (32 keys) inside key block (cq >> 1) of the P / dS tiles
     const uint32_t sP = sbase + BWD_SMEM_P + (cq >> 1) * 16384 + r * 128;
+    uint32_t g = 0;  // iterations processed by this CTA so far
+    int n = 0;       // items processed
 
     // TMEM accumulators -> global: dV_j / dK_j when a key tile is complete (warps 0-7 take dV,
     // warps 8-15 dK; 32 of the 64 columns each), dQ when the item is complete (thread group cq
     // takes columns (cq & 1) * 32 .. +32 of query tile cq >> 1). The drains of iteration g run
-    // inside iteration g+1, after its exp math and before its P / dS stores, so waiting for the
-    // MMAs of iteration g costs nothing.
-    auto drain = [&](int item, int j, bool key_tile_done, bool item_done) {
+    // inside iteration g+1, after its first exp math and before its P / dS stores, so waiting for
+    // the MMAs of iteration g costs nothing; at that point the P / dS region is idle, so each warp
+    // stages its 32 x 32 bf16 block there (64-byte swizzle) and hands it to a TMA store, which
+    // clips at the sequence end. (Per-thread 16-byte global stores hit 32 different lines per
+    // instruction and took ~2500 cycles per drain in the LSU.)
+    auto stage32 = [&](uint32_t dst, const uint32_t (&v)[32], float mul) {
+      const uint32_t base = dst + lane * 64;
+      const int sw = (lane >> 1) & 3;
+      const f32x2 m2 = pk2(mul, mul);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float x0, x1;
+          upk2(fmul2(pk2(__uint_as_float(v[8 * q4 + 2 * e]), __uint_as_float(v[8 * q4 + 2 * e + 1])), m2), x0, x1);
+          w[e] = pack_bf16(x0, x1);
+        }
+        sts128(base + ((q4 ^ sw) << 4), w[0], w[1], w[2], w[3]);
+      }
+    };
+    auto drain = [&](int item, int j, bool item_done) {
       const int h = item % p.H, b = item / p.H;
       const int sel = cq >> 1, cc = cq & 1;
-      if (key_tile_done) {
+      uint8_t* stg = smem + BWD_SMEM_P + warp * 4096;
+      {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(lane_addr + (sel == 0 ? COL_DV : COL_DK) + cc * 32, v);
@@ -483,62 +534,57 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_addr(sbar + 8 * 12);  // bar_dkv_free: accumulators are in registers
-        const int krow = j * 128 + r;
-        if (krow < p.Sk) {
-          const float mul = sel == 0 ? 1.0f : p.scale;
-          __nv_bfloat16* op = (sel == 0 ? p.dv : p.dk) +
-                              (static_cast<long long>(b) * p.Sk + krow) * (sel == 0 ? p.lddv : p.lddk) + h * 64 + cc * 32;
-#pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
-            o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
-            o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
-            o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
-            *reinterpret_cast<uint4*>(op + e) = o;
-          }
-        }
+        stage32(smem_u32(stg), v, sel == 0 ? 1.0f : p.scale);
       }
+      const bool dq_mine = item_done && sel < nq;
       if (item_done) {
         uint32_t v[32];
         __syncwarp();
-        if (sel < nq) {
+        if (dq_mine) {
           tmem_ld_32x32(lane_addr + COL_DQ + sel * 64 + cc * 32, v);
           tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_addr(sbar + 8 * 13);  // bar_dq_free
-        const int qrow = sel * 128 + r;
-        if (sel < nq && qrow < p.Sq) {
-          __nv_bfloat16* op = p.dq + (static_cast<long long>(b) * p.Sq + qrow) * p.lddq + h * 64 + cc * 32;
-#pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(v[e]) * p.scale, __uint_as_float(v[e + 1]) * p.scale);
-            o.y = pack_bf16(__uint_as_float(v[e + 2]) * p.scale, __uint_as_float(v[e + 3]) * p.scale);
-            o.z = pack_bf16(__uint_as_float(v[e + 4]) * p.scale, __uint_as_float(v[e + 5]) * p.scale);
-            o.w = pack_bf16(__uint_as_float(v[e + 6]) * p.scale, __uint_as_float(v[e + 7]) * p.scale);
-            *reinterpret_cast<uint4*>(op + e) = o;
-          }
-        }
+        if (dq_mine) stage32(smem_u32(stg) + 2048, v, p.scale);
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int row0 = (warp & 3) * 32, col0 = h * 64 + cc * 32;
+        tma_store_3d(sel == 0 ? &tmap_dv : &tmap_dk, stg, col0, j * 128 + row0, b);
+        if (dq_mine) tma_store_3d(&tmap_dq, stg + 2048, col0, sel * 128 + row0, b);
+        tma_store_commit();
+        tma_store_wait_read<0>();  // the staging block is about to be overwritten with P / dS
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * BWD_MATH_WARPS) : "memory");  // ... by any math warp
     };
 
-    uint32_t g = 0;
-    int n = 0;
+    // -lse * log2(e) of this thread's two query rows; the next item's values are fetched during
+    // the current item's last iteration
+    auto load_nlse = [&](int item, int i) {
+      const int qrow = i * 128 + r;
+      return (i < nq && qrow < p.Sq) ? -p.lse[static_cast<long long>(item) * p.Sq + qrow] * kLog2e : -INFINITY;
+    };
+    float nx0 = 0.f, nx1 = 0.f;
+    if (blockIdx.x < items) { nx0 = load_nlse(blockIdx.x, 0); nx1 = load_nlse(blockIdx.x, 1); }
+
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
-      float delta0 = 0.f, delta1 = 0.f, nlse0 = -INFINITY, nlse1 = -INFINITY;
+      float delta0 = 0.f, delta1 = 0.f;
+      const float nlse0 = nx0, nlse1 = nx1;  // lse is [B, H, Sq] = [item, Sq]; -inf on invalid rows -> p = 0
       for (int it = 0; it < nit; ++it, ++g) {
         const int j = it_j(it), i = it_i(it);
+        if (it == nit - 1 && item + static_cast<int>(gridDim.x) < items) {
+          nx0 = load_nlse(item + gridDim.x, 0);
+          nx1 = load_nlse(item + gridDim.x, 1);
+        }
         if (j == 0) {
-          // first use of query tile i: delta_i = sum_d O[i, d] * dO[i, d] from the staged tiles,
-          // and -lse * log2(e). Invalid query rows keep nlse = -inf, so their p = 2^(-inf) = 0.
+          // first use of query tile i: delta_i = sum_d O[i, d] * dO[i, d] from the staged tiles
           const int slq = alt ? (n & 1) : i;
           mbar_wait_parked_addr(sbar + 8 * slq, (alt ? n >> 1 : n) & 1);  // bar_ldq[slq]
-          const int qrow = i * 128 + r;
-          float dl = 0.f, nl = -INFINITY;
-          if (qrow < p.Sq) {
+          float dl = 0.f;
+          if (i * 128 + r < p.Sq) {
             const uint32_t so = sbase + BWD_SMEM_O + slq * BWD_TILE + r * 128;
             const uint32_t sd = sbase + BWD_SMEM_DO + slq * BWD_TILE + r * 128;
             f32x2 acc2 = pk2(0.f, 0.f);
@@ -555,32 +601,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             float a0, a1;
             upk2(acc2, a0, a1);
             dl = a0 + a1;
-            nl = -p.lse[(static_cast<long long>(item) * p.Sq) + qrow] * kLog2e;  // lse is [B, H, Sq]
           }
-          if (i == 0) { delta0 = dl; nlse0 = nl; } else { delta1 = dl; nlse1 = nl; }
+          if (i == 0) delta0 = dl; else delta1 = dl;
         }
+        if (threadIdx.x == 0) TRACE(16 * g + 8);
         mbar_wait_parked_addr(sbar + 8 * 8, g & 1);  // bar_sdp_full
+        if (threadIdx.x == 0) TRACE(16 * g + 9);
         tc_fence_after();
         const float sl2 = p.scale * kLog2e;
         const float dl = i ? delta1 : delta0, nl = i ? nlse1 : nlse0;
         const f32x2 sl2v = pk2(sl2, sl2), nlv = pk2(nl, nl), ndlv = pk2(-dl, -dl);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {  // four sub-chunks of 8 keys = one 16-byte P / dS store each
-          const int key0 = j * 128 + cq * 32 + c * 8;
-          uint32_t sv[8], dp[8], pp[4], dd[4];
-          const bool live = key0 < p.Sk;
-          __syncwarp();
-          if (live) {
-            tmem_ld_32x8(lane_addr + COL_S + cq * 32 + c * 8, sv);
-            tmem_ld_32x8(lane_addr + COL_DP + cq * 32 + c * 8, dp);
-            tmem_ld_wait();
-          }
-          if (c == 3) {  // S / dP of this iteration are in registers: the next S / dP MMAs may overwrite them
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_addr(sbar + 8 * 9);  // bar_sdp_read
-          }
-          if (live) {
+        const int keyb = j * 128 + cq * 32;  // this thread's first key
+        // 8 keys: P = 2^(S * scale * log2e - lse * log2e), dS = P * (dP - delta), one 16-byte store each
+        auto sub_chunk = [&](const uint32_t (&sv)[8], const uint32_t (&dp)[8], int c) {
+          const int key0 = keyb + c * 8;
+          uint32_t pp[4], dd[4];
+          if (key0 < p.Sk) {
             const bool full = key0 + 8 <= p.Sk;
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
@@ -592,7 +628,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 p1 = (key0 + e + 1 < p.Sk) ? p1 : 0.f;
               }
               pp[e >> 1] = pack_bf16(p0, p1);
-              float d0, d1;  // dS = P * (dP - delta)
+              float d0, d1;
               upk2(fmul2(pk2(p0, p1), fadd2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ndlv)), d0, d1);
               dd[e >> 1] = pack_bf16(d0, d1);
             }
@@ -603,32 +639,70 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if (c == 0 && g > 0) {
             // the math above overlapped the previous iteration's dV / dK / dQ MMAs; the stores need
             // their P / dS operands consumed, and that iteration's finished accumulators are drained
+            if (threadIdx.x == 0) TRACE(16 * g + 10);
             mbar_wait_parked_addr(sbar + 8 * 11, (g - 1) & 1);  // bar_pds_free
+            if (threadIdx.x == 0) TRACE(16 * g + 11);
             tc_fence_after();
-            if (it == 0) drain(item - static_cast<int>(gridDim.x), nk - 1, true, true);
-            else if (i == 0) drain(item, j - 1, true, false);
+            if (it == 0) drain(item - static_cast<int>(gridDim.x), nk - 1, true);
+            else if (i == 0) drain(item, j - 1, false);
           }
           const int sw = (((cq & 1) * 4 + c) ^ (r & 7)) << 4;
           sts128(sP + sw, pp[0], pp[1], pp[2], pp[3]);
           sts128(sP + (BWD_SMEM_DS - BWD_SMEM_P) + sw, dd[0], dd[1], dd[2], dd[3]);
+        };
+        const uint32_t ts = lane_addr + COL_S + cq * 32, td = lane_addr + COL_DP + cq * 32;
+        {
+          uint32_t sv[8], dp[8];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            __syncwarp();
+            if (keyb + c * 8 < p.Sk) {
+              tmem_ld_32x8(ts + c * 8, sv);
+              tmem_ld_32x8(td + c * 8, dp);
+              tmem_ld_wait();
+            }
+            sub_chunk(sv, dp, c);
+          }
+        }
+        {
+          // the last two sub-chunks are fetched together, so S / dP can be handed back to the MMA
+          // warp (next iteration's S / dP) with half of this iteration's exp math still to do
+          uint32_t sv2[8], dp2[8], sv3[8], dp3[8];
+          __syncwarp();
+          if (keyb + 16 < p.Sk) {
+            tmem_ld_32x8(ts + 16, sv2);
+            tmem_ld_32x8(td + 16, dp2);
+            if (keyb + 24 < p.Sk) {
+              tmem_ld_32x8(ts + 24, sv3);
+              tmem_ld_32x8(td + 24, dp3);
+            }
+            tmem_ld_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_addr(sbar + 8 * 9);  // bar_sdp_read
+          sub_chunk(sv2, dp2, 2);
+          sub_chunk(sv3, dp3, 3);
         }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
+        if (threadIdx.x == 0) TRACE(16 * g + 12);
         if (lane == 0) mbar_arrive_addr(sbar + 8 * 10);  // bar_pds_ready: one arrival per warp
       }
     }
     if (g > 0) {  // the CTA's last item
       mbar_wait_parked_addr(sbar + 8 * 11, (g - 1) & 1);
       tc_fence_after();
-      drain(blockIdx.x + (n - 1) * static_cast<int>(gridDim.x), nk - 1, true, true);
+      drain(blockIdx.x + (n - 1) * static_cast<int>(gridDim.x), nk - 1, true);
+      if (lane == 0) tma_store_wait_all();
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == BWD_WARP_TMA) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem);
+    tmem_dealloc<512>(0u);
   }
 }
 
@@ -766,6 +840,12 @@ int make_head_map(CUtensorMap* m, const void* base, int B, int S, int H, long lo
 
 using namespace vitssl;
 
+#ifdef VITSSL_ATTN_TRACE
+extern "C" int vitssl_debug_attn_trace(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" int vitssl_attention_supported(int64_t Sq, int64_t Sk, int64_t d_head) {
   return (d_head == 64 && Sk >= 1 && Sk <= 256 && Sq >= 1) ? 1 : 0;
 }
@@ -829,6 +909,15 @@ extern "C" int vitssl_attention_bwd(const void* q, const void* k, const void* v,
   if ((rc = make_head_map(&mv, v, p.B, p.Sk, p.H, ldv, 128))) return rc;
   if ((rc = make_head_map(&mdo, d_out, p.B, p.Sq, p.H, ldo, 128))) return rc;
   if ((rc = make_head_map(&mo, out, p.B, p.Sq, p.H, ldo, 128))) return rc;
+  // outputs leave through 32-column x 32-row staging blocks (64-byte swizzle), clipped at S
+  CUtensorMap mdq, mdk, mdv;
+  auto out_map = [&](CUtensorMap* m, void* base, int S, long long ld) {
+    return make_tmap_bf16_3d_sw(m, base, (uint64_t)p.H * 64, (uint64_t)S, (uint64_t)p.B, (uint64_t)ld * 2,
+                                (uint64_t)S * ld * 2, 32, 32, 1, 64);
+  };
+  if ((rc = out_map(&mdq, dq, p.Sq, lddq))) return rc;
+  if ((rc = out_map(&mdk, dk, p.Sk, lddk))) return rc;
+  if ((rc = out_map(&mdv, dv, p.Sk, lddv))) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
@@ -837,7 +926,7 @@ extern "C" int vitssl_attention_bwd(const void* q, const void* k, const void* v,
   }
   const long long items = (long long)B * H;  // persistent: one CTA per SM walks the (batch, head) items
   const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
-  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(mq, mk, mv, mdo, mo, p);
+  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(mq, mk, mv, mdo, mo, mdq, mdk, mdv, p);
   return check_launch("attention_bwd");
 }
 

@@ -384,6 +384,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
       "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -590,5 +597,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t in
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2,
                       uint64_t ld1_bytes, uint64_t ld2_bytes, uint32_t box_inner, uint32_t box_d1,
                       uint32_t box_d2);
+int make_tmap_bf16_3d_sw(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2,
+                         uint64_t ld1_bytes, uint64_t ld2_bytes, uint32_t box_inner, uint32_t box_d1,
+                         uint32_t box_d2, int swizzle_bytes);
 
 }  // namespace vitssl
