@@ -251,6 +251,19 @@ __device__ __forceinline__ f32x2 normal_cdf2_sat(float x0, float x1) {
   return pk2(r0, r1);
 }
 
+// One lane of a converged warp (always the same one). Unlike `if (lane == 0)`, the compiler knows
+// the branch is taken by a single elected lane of a warp in uniform control flow, so operands
+// computed from warp-uniform values stay in uniform registers (tcgen05.mma / TMA operands).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------
