@@ -49,7 +49,8 @@ int64_t vitssl_launch_count(int reset);
  * epilogue: NONE | BIAS (+bias[N]) | BIAS_GELU (aux <- bf16(acc+bias), C <- dropout(gelu(aux));
  *           feed_forward.py:26-27) | DGELU (C <- acc * mask/(1-p) * gelu'(aux)).
  * out_fp32: C is fp32, else bf16. split_k: 0 = off, -1 = auto, n = n splits (fp32 NONE only;
- * C is zeroed on `stream` and accumulated with red.add). */
+ * C is zeroed on `stream` and the partial sums are accumulated with TMA reduce-add), -2 = auto
+ * with C already zeroed by the caller (one memset can then serve many GEMMs). */
 #define VITSSL_EPI_NONE 0
 #define VITSSL_EPI_BIAS 1
 #define VITSSL_EPI_BIAS_GELU 2
@@ -78,6 +79,13 @@ int vitssl_add_layernorm_bwd(const void* dy, const float* x, int64_t ldx, const 
                              int64_t ld_dres, float* dx, int64_t ld_dx, void* dbranch,
                              float* dgamma, float* dbeta, int64_t rows, int64_t D, float dropout_p,
                              uint64_t philox_seed, uint64_t philox_offset, vitssl_stream_t stream);
+/* same, but dgamma/dbeta are accumulated into (the caller zeroed them, e.g. with one memset for
+ * every layer's gradients) */
+int vitssl_add_layernorm_bwd_acc(const void* dy, const float* x, int64_t ldx, const float* mean,
+                                 const float* rstd, const float* gamma, const float* dres,
+                                 int64_t ld_dres, float* dx, int64_t ld_dx, void* dbranch,
+                                 float* dgamma, float* dbeta, int64_t rows, int64_t D, float dropout_p,
+                                 uint64_t philox_seed, uint64_t philox_offset, vitssl_stream_t stream);
 
 /* ---- multi-head attention (attention.py:5-27, 86-103) -----------------------------------
  * q/k/v/out are bf16 [B, S, H, 64] views: token rows of pitch ld* elements, head h at column
@@ -141,6 +149,7 @@ typedef struct {
   float* dx;                           /* fp32 [B*S, D] gradient of x_in */
   void* dbranch; void* du; void* dxn; void* dctx; void* dqkv;  /* bf16 scratch: [M,D] [M,F] [M,D] [M,D] [M,3D] */
   float* gs[2];                        /* fp32 [B*S, D] scratch (stream gradient ping-pong) */
+  /* parameter gradients: ACCUMULATED into — every buffer below must be zero on entry */
   float* const* dwqkv; float* const* dwo; float* const* dw1; float* const* db1;
   float* const* dw2; float* const* db2;
   float* const* dg1; float* const* dbe1; float* const* dg2; float* const* dbe2;
@@ -158,6 +167,9 @@ int vitssl_multi_ema(void* const* host_teacher, const void* const* host_student,
 /* out[c] = sum_r x[r,c] (bf16 in, fp32 out; out is zeroed on `stream`): bias gradients. */
 int vitssl_colsum_bf16(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out,
                        vitssl_stream_t stream);
+/* out[c] += sum_r x[r,c] (out zeroed by the caller) */
+int vitssl_colsum_bf16_acc(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out,
+                           vitssl_stream_t stream);
 
 /* ---- patches and tokens ------------------------------------------------------------------ */
 /* img fp32 [B,C,H,W] -> bf16 [B*(H/p)*(W/p), C*p*p], feature order (c,ph,pw), patches row-major

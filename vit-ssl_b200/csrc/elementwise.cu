@@ -331,6 +331,56 @@ __global__ void __launch_bounds__(128) embed_bwd_kernel(const EmbedBwdArgs a) {
   }
 }
 
+// Same, for D <= 1024 with a mask token: every thread of the grid would otherwise add its masked
+// partial sums onto the same D addresses (thousands of colliding global atomics per address, which
+// made this the slowest elementwise kernel of the SimMIM step). The CTA first folds its tokens
+// together in shared memory and then issues one global atomic per feature.
+__global__ void __launch_bounds__(128) embed_bwd_masktoken_kernel(const EmbedBwdArgs a) {
+  __shared__ float sm_tok[1024];
+  for (int i = threadIdx.x; i < a.D; i += 128) sm_tok[i] = 0.f;
+  __syncthreads();
+  const int d8 = a.D / 8;
+  const int g = blockIdx.x * 128 + threadIdx.x;
+  if (g < a.S * d8) {
+    const int d = (g % d8) * 8, s = g / d8;
+    const int b0 = blockIdx.y * a.b_per_cta, b1 = min(a.B, b0 + a.b_per_cta);
+    float accp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float accm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool is_cls = a.has_cls && s == 0;
+#pragma unroll 4
+    for (int b = b0; b < b1; ++b) {
+      const float* src = a.dx + b * a.ld_b + s * a.ld_s + d;
+      const float4 v0 = *reinterpret_cast<const float4*>(src);
+      const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) accp[i] += v[i];
+      if (!is_cls) {
+        const long long pr = static_cast<long long>(b) * a.N + (s - a.has_cls);
+        const bool m = a.mask[pr];
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (m) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) accm[i] += v[i];
+        } else {
+          o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+          o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+        }
+        *reinterpret_cast<uint4*>(a.dproj + pr * a.D + d) = o;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(a.dpos + static_cast<long long>(s) * a.D + d + i, accp[i]);
+    if (!is_cls) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sm_tok[d + i], accm[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.D; i += 128)
+    if (sm_tok[i] != 0.f) atomicAdd(a.dmask_token + i, sm_tok[i]);
+}
+
 // out[i,:] = bf16(x[idx[i], :])   (ssl/simmim/model.py:56 boolean-mask gather, sync-free)
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ x, long long ldx,
                                                           const int* __restrict__ idx,
@@ -403,6 +453,12 @@ extern "C" int vitssl_colsum_bf16(const void* x, int64_t ld, int64_t rows, int64
                                   cudaStream_t stream) {
   VITSSL_REQUIRE(x && out && rows >= 0 && cols > 0, VITSSL_ERR_ARG, "colsum_bf16: bad args");
   cudaMemsetAsync(out, 0, cols * sizeof(float), stream);
+  return vitssl_colsum_bf16_acc(x, ld, rows, cols, out, stream);
+}
+
+extern "C" int vitssl_colsum_bf16_acc(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out,
+                                      cudaStream_t stream) {
+  VITSSL_REQUIRE(x && out && rows >= 0 && cols > 0, VITSSL_ERR_ARG, "colsum_bf16: bad args");
   if (rows == 0) return 0;
   const bool fast = (cols % 8 == 0) && (ld % 8 == 0) && aligned16(x);
   if (fast && ld == cols && cols / 8 <= 288) {
@@ -497,7 +553,8 @@ extern "C" int vitssl_embed_tokens_bwd(const float* dx, int64_t ld_b, int64_t ld
   if (splits < 1) splits = 1;
   a.b_per_cta = (int)((B + splits - 1) / splits);
   dim3 grid(gx, (unsigned)((B + a.b_per_cta - 1) / a.b_per_cta));
-  embed_bwd_kernel<<<grid, 128, 0, stream>>>(a);
+  if (dmask_token && mask && D <= 1024) embed_bwd_masktoken_kernel<<<grid, 128, 0, stream>>>(a);
+  else embed_bwd_kernel<<<grid, 128, 0, stream>>>(a);
   return check_launch("embed_tokens_bwd");
 }
 

@@ -71,7 +71,7 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
   const float p = f->dropout_p;
   const float scale = 0.125f;
   // gradient of the final add: the stream gradient passes through, the branch gets mask/(1-p) * g
-  VITSSL_TRY(vitssl_add_layernorm_bwd(nullptr, nullptr, 0, nullptr, nullptr, nullptr, a->gout, D, nullptr, 0,
+  VITSSL_TRY(vitssl_add_layernorm_bwd_acc(nullptr, nullptr, 0, nullptr, nullptr, nullptr, a->gout, D, nullptr, 0,
                                       a->dbranch, nullptr, nullptr, M, D, p, f->seed, (uint64_t)(3 * L - 1), stream));
   const float* gs = a->gout;  // gradient on the residual stream
   for (int64_t l = L - 1; l >= 0; --l) {
@@ -80,23 +80,23 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
     VITSSL_TRY(vitssl_gemm_bf16(dy2, f->w2[l], a->du, M, F, D, D, F, F, 0, 1, VITSSL_EPI_DGELU, nullptr, f->u[l], F,
                                 1.0f, 0, 0, p, f->seed, (uint64_t)(3 * l + 1), stream));
     VITSSL_TRY(vitssl_gemm_bf16(dy2, f->h[l], a->dw2[l], D, F, M, D, F, F, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
-                                1.0f, 1, -1, 0.f, 0, 0, stream));
-    VITSSL_TRY(vitssl_colsum_bf16(dy2, D, M, D, a->db2[l], stream));
+                                1.0f, 1, -2, 0.f, 0, 0, stream));
+    VITSSL_TRY(vitssl_colsum_bf16_acc(dy2, D, M, D, a->db2[l], stream));
     VITSSL_TRY(vitssl_gemm_bf16(a->du, f->w1[l], a->dxn, M, D, F, F, D, D, 0, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
                                 1.0f, 0, 0, 0.f, 0, 0, stream));
     VITSSL_TRY(vitssl_gemm_bf16(a->du, f->xn2[l], a->dw1[l], F, D, M, F, D, D, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr,
-                                0, 1.0f, 1, -1, 0.f, 0, 0, stream));
-    VITSSL_TRY(vitssl_colsum_bf16(a->du, F, M, F, a->db1[l], stream));
+                                0, 1.0f, 1, -2, 0.f, 0, 0, stream));
+    VITSSL_TRY(vitssl_colsum_bf16_acc(a->du, F, M, F, a->db1[l], stream));
     // LN2 + residual: gs <- d(xmid), dy1 = dropout-masked gradient of the attention branch
     float* gs_mid = a->gs[0];
-    VITSSL_TRY(vitssl_add_layernorm_bwd(a->dxn, f->xmid[l], D, f->mean2[l], f->rstd2[l], f->g2[l], gs, D, gs_mid, D,
+    VITSSL_TRY(vitssl_add_layernorm_bwd_acc(a->dxn, f->xmid[l], D, f->mean2[l], f->rstd2[l], f->g2[l], gs, D, gs_mid, D,
                                         a->dbranch, a->dg2[l], a->dbe2[l], M, D, p, f->seed, (uint64_t)(3 * l),
                                         stream));
     const void* dy1 = a->dbranch;
     VITSSL_TRY(vitssl_gemm_bf16(dy1, f->wo[l], a->dctx, M, D, D, D, D, D, 0, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
                                 1.0f, 0, 0, 0.f, 0, 0, stream));
     VITSSL_TRY(vitssl_gemm_bf16(dy1, f->ctx[l], a->dwo[l], D, D, M, D, D, D, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
-                                1.0f, 1, -1, 0.f, 0, 0, stream));
+                                1.0f, 1, -2, 0.f, 0, 0, stream));
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(f->qkv[l]);
     __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv);
     VITSSL_TRY(vitssl_attention_bwd(qkv, qkv + D, qkv + 2 * D, 3 * D, 3 * D, 3 * D, f->ctx[l], a->dctx, D, f->lse[l],
@@ -104,11 +104,11 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
     VITSSL_TRY(vitssl_gemm_bf16(dqkv, f->wqkv[l], a->dxn, M, D, 3 * D, 3 * D, D, D, 0, 1, VITSSL_EPI_NONE, nullptr,
                                 nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));
     VITSSL_TRY(vitssl_gemm_bf16(dqkv, f->xn1[l], a->dwqkv[l], 3 * D, D, M, 3 * D, D, D, 1, 1, VITSSL_EPI_NONE, nullptr,
-                                nullptr, 0, 1.0f, 1, -1, 0.f, 0, 0, stream));
+                                nullptr, 0, 1.0f, 1, -2, 0.f, 0, 0, stream));
     // LN1 + residual: gs <- d(block input); for l > 0 also the masked gradient of block l-1's FFN
     const float* x_l = (l == 0) ? f->x_in : f->xs[l];
     float* gs_in = (l == 0) ? a->dx : a->gs[1];
-    VITSSL_TRY(vitssl_add_layernorm_bwd(a->dxn, x_l, D, f->mean1[l], f->rstd1[l], f->g1[l], gs_mid, D, gs_in, D,
+    VITSSL_TRY(vitssl_add_layernorm_bwd_acc(a->dxn, x_l, D, f->mean1[l], f->rstd1[l], f->g1[l], gs_mid, D, gs_in, D,
                                         l > 0 ? a->dbranch : nullptr, a->dg1[l], a->dbe1[l], M, D, l > 0 ? p : 0.f,
                                         f->seed, (uint64_t)(l > 0 ? 3 * l - 1 : 0), stream));
     gs = gs_in;

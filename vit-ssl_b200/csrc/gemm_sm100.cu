@@ -851,7 +851,7 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   e.atomic = s.splits > 1 ? 1 : 0;
   e.vec_ok = out_ok ? 1 : 0;
   e.tma_out = out_ok ? 1 : 0;  // split-K partials go through the same staging tiles as a TMA reduce-add
-  if (e.atomic) {
+  if (e.atomic && split_k != -2) {  // -2: the caller hands over a zeroed C (one memset for many GEMMs)
     cudaError_t err = cudaMemset2DAsync(C, ldc * 4, 0, N * 4, M, stream);
     if (err != cudaSuccess) {
       set_error("gemm: memset failed: %s", cudaGetErrorString(err));

@@ -386,15 +386,26 @@ extern "C" int vitssl_add_layernorm_bwd(const void* dy, const float* x, int64_t 
                                         int64_t rows, int64_t D, float dropout_p,
                                         uint64_t philox_seed, uint64_t philox_offset,
                                         cudaStream_t stream) {
+  if (dgamma && dbeta && D > 0) {
+    cudaMemsetAsync(dgamma, 0, D * sizeof(float), stream);
+    cudaMemsetAsync(dbeta, 0, D * sizeof(float), stream);
+  }
+  return vitssl_add_layernorm_bwd_acc(dy, x, ldx, mean, rstd, gamma, dres, ld_dres, dx, ld_dx, dbranch, dgamma,
+                                      dbeta, rows, D, dropout_p, philox_seed, philox_offset, stream);
+}
+
+extern "C" int vitssl_add_layernorm_bwd_acc(const void* dy, const float* x, int64_t ldx,
+                                            const float* mean, const float* rstd, const float* gamma,
+                                            const float* dres, int64_t ld_dres, float* dx,
+                                            int64_t ld_dx, void* dbranch, float* dgamma, float* dbeta,
+                                            int64_t rows, int64_t D, float dropout_p,
+                                            uint64_t philox_seed, uint64_t philox_offset,
+                                            cudaStream_t stream) {
   VITSSL_REQUIRE(rows >= 0 && D > 0, VITSSL_ERR_ARG, "add_layernorm_bwd: bad args");
   if (dy) VITSSL_REQUIRE(x && mean && rstd && gamma, VITSSL_ERR_ARG, "add_layernorm_bwd: LN inputs missing");
   VITSSL_REQUIRE(dy || dres, VITSSL_ERR_ARG, "add_layernorm_bwd: no incoming gradient");
   VITSSL_REQUIRE(dx || dbranch, VITSSL_ERR_ARG, "add_layernorm_bwd: no output requested");
   VITSSL_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), VITSSL_ERR_ARG, "dgamma/dbeta go together");
-  if (dgamma) {
-    cudaMemsetAsync(dgamma, 0, D * sizeof(float), stream);
-    cudaMemsetAsync(dbeta, 0, D * sizeof(float), stream);
-  }
   if (rows == 0) return 0;
   LnBwdArgs a{};
   a.dy = reinterpret_cast<const __nv_bfloat16*>(dy); a.x = x; a.ldx = ldx; a.mean = mean;

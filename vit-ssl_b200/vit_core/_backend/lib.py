@@ -30,6 +30,7 @@ SIGNATURES["vitssl_gemm_bf16"] = "ppp" + "llllll" + "iii" + "pp" + "l" + "f" + "
 
 SIGNATURES["vitssl_add_layernorm_fwd"] = "plpp" + "pp" + "ppp" + "ll" + "ff" + "uu" + "s"
 SIGNATURES["vitssl_add_layernorm_bwd"] = "ppl" + "ppp" + "pl" + "pl" + "p" + "pp" + "ll" + "f" + "uu" + "s"
+SIGNATURES["vitssl_add_layernorm_bwd_acc"] = SIGNATURES["vitssl_add_layernorm_bwd"]
 SIGNATURES["vitssl_attention_supported"] = "lll"
 SIGNATURES["vitssl_attention_fwd"] = "ppp" + "lll" + "pl" + "p" + "llll" + "f" + "s"
 SIGNATURES["vitssl_attention_bwd"] = "ppp" + "lll" + "ppl" + "p" + "pl" + "pl" + "pl" + "llll" + "f" + "s"
@@ -40,6 +41,7 @@ SIGNATURES["vitssl_encoder_stack_bwd"] = "ps"
 SIGNATURES["vitssl_multi_cast_bf16"] = "pppis"
 SIGNATURES["vitssl_multi_ema"] = "pppifs"
 SIGNATURES["vitssl_colsum_bf16"] = "plllps"
+SIGNATURES["vitssl_colsum_bf16_acc"] = "plllps"
 SIGNATURES["vitssl_im2col_bf16"] = "pp" + "lllll" + "s"
 SIGNATURES["vitssl_gather_patches_f32"] = "ppp" + "lllll" + "s"
 SIGNATURES["vitssl_embed_tokens_fwd"] = "pppppp" + "lll" + "s"

@@ -561,12 +561,17 @@ def encoder_stack_bwd(st, gout):
     du = torch.empty((M, F_), device=dev, dtype=bf)
     dqkv = torch.empty((M, 3 * D), device=dev, dtype=bf)
     gs = torch.empty((2, M, D), device=dev, dtype=f32)
-    g = {"dwqkv": torch.empty((L, 3 * D, D), device=dev, dtype=f32), "dwo": torch.empty((L, D, D), device=dev, dtype=f32),
-         "dw1": torch.empty((L, F_, D), device=dev, dtype=f32), "db1": torch.empty((L, F_), device=dev, dtype=f32),
-         "dw2": torch.empty((L, D, F_), device=dev, dtype=f32), "db2": torch.empty((L, D), device=dev, dtype=f32)}
-    ln = torch.empty((4, L, D), device=dev, dtype=f32)
-    for i, name in enumerate(("dg1", "dbe1", "dg2", "dbe2")):
-        g[name] = ln[i]
+    # every parameter gradient of the stack lives in ONE zeroed fp32 buffer: the C side accumulates
+    # into it (split-K TMA reduce-adds, column sums, LayerNorm dgamma/dbeta), so a single fill
+    # replaces ~125 per-kernel memsets per step
+    shapes = {"dwqkv": (L, 3 * D, D), "dwo": (L, D, D), "dw1": (L, F_, D), "db1": (L, F_), "dw2": (L, D, F_),
+              "db2": (L, D), "dg1": (L, D), "dbe1": (L, D), "dg2": (L, D), "dbe2": (L, D)}
+    sizes = {k: int(torch.Size(v).numel()) for k, v in shapes.items()}
+    flat = torch.zeros((sum(sizes.values()),), device=dev, dtype=f32)
+    g, off = {}, 0
+    for k, shp in shapes.items():
+        g[k] = flat[off:off + sizes[k]].view(shp)
+        off += sizes[k]
     b = _EncBwdArgs()
     b.fwd = _ct.pointer(st.args)
     b.gout, b.dx = _p(gout), _p(dx)
