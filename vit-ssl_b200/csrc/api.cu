@@ -7,6 +7,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "vitssl_b200.h"
 
@@ -31,6 +33,13 @@ int check_launch(const char* what) {
     return VITSSL_ERR_CUDA;
   }
   return VITSSL_OK;
+}
+
+bool pdl_enabled() {
+  // measured neutral on the SimMIM step (15.68-15.87 ms with, 15.75-15.87 ms without: the hot kernels
+  // fill every SM with one persistent CTA, so a dependent grid cannot become resident early) -> opt-in
+  static const bool on = getenv("VITSSL_PDL") && atoi(getenv("VITSSL_PDL")) != 0;
+  return on;
 }
 
 int num_sms() {

@@ -64,6 +64,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bar_oread = bar + 5;   // O drained: TMEM reusable for the next item's S
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 6);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = (p.Sq + 127) / 128;
   const int items = p.B * p.H * nq;
@@ -82,6 +83,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // the prologue overlapped the previous kernel's tail; global memory from here on
   const uint32_t kv_bytes = static_cast<uint32_t>(p.kv_rows) * 128u;
 
   if (warp == 4) {
@@ -335,6 +337,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bar_dq_free = bar + 13;    // dQ accumulators drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 14);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = (p.Sq + 127) >> 7, nk = (p.Sk + 127) >> 7;  // each 1 or 2
   const int nit = nq * nk;
@@ -369,6 +372,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (threadIdx.x == 0) printf("vitssl: attention_bwd expects the TMEM allocation at column 0\n");
     __trap();
   }
+  pdl_wait();  // the prologue overlapped the previous kernel's tail; global memory from here on
   constexpr uint32_t tmem = 0;
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
 
@@ -880,7 +884,8 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
   const long long items = (long long)B * H * ((Sq + 127) / 128);
   const long long slots = 2ll * num_sms();  // persistent: two CTAs per SM
   const unsigned grid = (unsigned)(items < slots ? items : slots);
-  attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM_BYTES, stream>>>(mq, mk, mv, p);
+  cudaError_t lerr = launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, p);
+  if (lerr != cudaSuccess) { set_error("attention_fwd: launch failed: %s", cudaGetErrorString(lerr)); return VITSSL_ERR_CUDA; }
   return check_launch("attention_fwd");
 }
 
@@ -926,7 +931,9 @@ extern "C" int vitssl_attention_bwd(const void* q, const void* k, const void* v,
   }
   const long long items = (long long)B * H;  // persistent: one CTA per SM walks the (batch, head) items
   const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
-  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(mq, mk, mv, mdo, mo, mdq, mdk, mdv, p);
+  cudaError_t lerr = launch_pdl(attn_bwd_kernel, dim3(grid), dim3(BWD_THREADS), BWD_SMEM_BYTES, stream, mq, mk, mv, mdo, mo,
+                                mdq, mdk, mdv, p);
+  if (lerr != cudaSuccess) { set_error("attention_bwd: launch failed: %s", cudaGetErrorString(lerr)); return VITSSL_ERR_CUDA; }
   return check_launch("attention_bwd");
 }
 

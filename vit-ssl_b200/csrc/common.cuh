@@ -34,6 +34,24 @@ enum : int {
 };
 
 int num_sms();  // cached SM count of the current device
+bool pdl_enabled();  // programmatic dependent launch for the hot kernels (VITSSL_PDL=0 disables)
+
+// Launch with programmatic stream serialization: the grid may begin (prologue: barrier init,
+// TMEM allocation, descriptor prefetch, launch latency) while the previous kernel on the stream
+// is still draining; the kernel itself calls pdl_wait() before its first global-memory access,
+// which blocks until that kernel has completed and its writes are visible. Only kernels that
+// contain pdl_wait() may be launched this way.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ----------------------------------------------------------------------------------
 // Small device helpers
@@ -42,6 +60,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// programmatic dependent launch (see launch_pdl): let the next kernel on the stream start its
+// prologue now / wait for the previous kernel's completion and memory flush
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(288) colsum_dense_kernel(const __nv_bfloat16* __restrict__ x, long long rows,
                                                            int g, float* __restrict__ out, int rows_per_cta) {
   extern __shared__ float red[];  // [blockDim.x][8]
+  pdl_launch_dependents();
+  pdl_wait();
   const int k = blockDim.x / g;   // rows per pass
   const int cg = threadIdx.x % g, rl = threadIdx.x / g;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
@@ -471,8 +473,8 @@ extern "C" int vitssl_colsum_bf16_acc(const void* x, int64_t ld, int64_t rows, i
       if (ctas > max_ctas) ctas = max_ctas;
       const int rows_per_cta = (int)((((rows + ctas - 1) / ctas) + k - 1) / k * k);
       const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
-      colsum_dense_kernel<<<grid, threads, threads * 8 * sizeof(float), stream>>>(
-          (const __nv_bfloat16*)x, rows, g, out, rows_per_cta);
+      launch_pdl(colsum_dense_kernel, dim3(grid), dim3(threads), threads * 8 * sizeof(float), stream,
+                 (const __nv_bfloat16*)x, (long long)rows, g, out, rows_per_cta);
       return check_launch("colsum_bf16");
     }
   }

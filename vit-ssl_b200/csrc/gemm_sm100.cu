@@ -442,6 +442,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // rank 0 of a pair issues the MMAs
@@ -479,6 +480,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
 
   const int num_work = s.m_tiles * s.n_tiles * s.splits;
 
@@ -716,10 +718,12 @@ int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::smem_bytes(e.tma_out != 0);
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t err = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tx, s, e);
     if (err != cudaSuccess) {
       set_error("gemm: cluster launch failed: %s", cudaGetErrorString(err));
@@ -728,7 +732,12 @@ int launch_tcgen05(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     return check_launch("gemm_tcgen05_pair");
   } else {
     const int grid = num_work < num_sms() ? num_work : num_sms();
-    kern<<<grid, GEMM_THREADS, Cfg::smem_bytes(e.tma_out != 0), stream>>>(ta, tb, tc, tx, s, e);
+    cudaError_t err = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::smem_bytes(e.tma_out != 0), stream, ta, tb,
+                                 tc, tx, s, e);
+    if (err != cudaSuccess) {
+      set_error("gemm: launch failed: %s", cudaGetErrorString(err));
+      return VITSSL_ERR_CUDA;
+    }
     return check_launch("gemm_tcgen05");
   }
 }

@@ -85,6 +85,8 @@ __device__ __forceinline__ Vec8 dropout_mult8(unsigned long long seed, unsigned 
 
 template <int NG>  // NG = ceil(D / 256), D % 8 == 0
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnFwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const f32x2 zero = pk2(0.f, 0.f);
   // grid-stride over rows: a few resident CTAs per SM stream the whole tensor
@@ -202,6 +204,8 @@ struct LnBwdArgs {
 template <int NG>
 __global__ void __launch_bounds__(LN_WARPS * 32, NG <= 2 ? 4 : 2) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float red[LN_WARPS][NG * 256 + 8];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const f32x2 zero = pk2(0.f, 0.f);
   Vec8 dg[NG], db[NG];
@@ -368,10 +372,10 @@ extern "C" int vitssl_add_layernorm_fwd(const float* x, int64_t ldx, const void*
   if (fast) {
     const int ng = (int)((D + 255) / 256);
     switch (ng) {
-      case 1: ln_fwd_kernel<1><<<grid, LN_WARPS * 32, 0, stream>>>(a); break;
-      case 2: ln_fwd_kernel<2><<<grid, LN_WARPS * 32, 0, stream>>>(a); break;
-      case 3: ln_fwd_kernel<3><<<grid, LN_WARPS * 32, 0, stream>>>(a); break;
-      default: ln_fwd_kernel<4><<<grid, LN_WARPS * 32, 0, stream>>>(a); break;
+      case 1: launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, a); break;
+      case 2: launch_pdl(ln_fwd_kernel<2>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, a); break;
+      case 3: launch_pdl(ln_fwd_kernel<3>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, a); break;
+      default: launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, a); break;
     }
   } else {
     ln_fwd_generic_kernel<<<(unsigned)want_f, LN_WARPS * 32, 0, stream>>>(a);
@@ -424,10 +428,10 @@ extern "C" int vitssl_add_layernorm_bwd_acc(const void* dy, const float* x, int6
   if (fast) {
     const int ng = (int)((D + 255) / 256);
     switch (ng) {
-      case 1: ln_bwd_kernel<1><<<grid, LN_WARPS * 32, 0, stream>>>(a); break;
-      case 2: ln_bwd_kernel<2><<<grid, LN_WARPS * 32, 0, stream>>>(a); break;
-      case 3: ln_bwd_kernel<3><<<grid, LN_WARPS * 32, 0, stream>>>(a); break;
-      default: ln_bwd_kernel<4><<<grid, LN_WARPS * 32, 0, stream>>>(a); break;
+      case 1: launch_pdl(ln_bwd_kernel<1>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, a); break;
+      case 2: launch_pdl(ln_bwd_kernel<2>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, a); break;
+      case 3: launch_pdl(ln_bwd_kernel<3>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, a); break;
+      default: launch_pdl(ln_bwd_kernel<4>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, a); break;
     }
   } else {
     ln_bwd_generic_kernel<<<grid, LN_WARPS * 32, 0, stream>>>(a);
