@@ -37,6 +37,16 @@ VIT_S = dict(embed_dim=384, num_blocks=12, num_heads=6, mlp_dim=1536, patch_size
 METRIC = "pretrain images/sec ViT-S/16 SimMIM (224x224, mask 0.6, batch 256/GPU)"
 
 
+def traffic(family):
+    """DRAM bytes per launch (mean over the family's launches of one step) from the committed ncu
+    launch list (profiles/traffic.json, written by scripts/summarize_launches.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))[family]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -295,13 +305,27 @@ def run_gpu_arm(args):
     if rank == 0:
         pk = peaks()
         gemm = [(a.elapsed_time(b), w) for (k, a, b, w) in recs if k.startswith("gemm")]
+
+        def gemm_bytes(kind):  # "gemm|MxNxK|a_mn=. b_mn=. epi=.": operands read once + result written once
+            try:
+                _, shp, flags = kind.split("|")
+                M_, N_, K_ = (int(v) for v in shp.split("x"))
+                fl = dict(kv.split("=") for kv in flags.split())
+                out_b = 4 if fl.get("a_mn") == "1" else 2  # weight gradients are fp32
+                return 2 * (M_ * K_ + N_ * K_) + M_ * N_ * out_b + (2 * M_ * N_ if fl.get("epi") in ("2", "3") else 0)
+            except Exception:
+                return None
+        gemm_b = [v for v in (gemm_bytes(k) for (k, *_r) in recs if k.startswith("gemm")) if v]
         ln = [(a.elapsed_time(b), w) for (k, a, b, w) in recs if k == "add_layernorm"]
         if gemm:
             t = sum(x for x, _ in gemm); f = sum(w for _, w in gemm)
             ach = f / (t * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all linear layers, fwd+dgrad+wgrad)",
                     "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                    "frac": round(ach / pk["tf_sustained"], 4), "traffic": traffic("gemm_tcgen05_kernel"),
+                    "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, mean over the family; profiles/traffic.json)",
+                    "algorithmic_bytes_per_launch": round(sum(gemm_b) / len(gemm_b)) if gemm_b else None,
+                    "peak_source": pk["src"] + " sustained bf16",
                     "launches_per_step": len(gemm), "ms_per_step_in_kernel": round(t, 3),
                     "share_of_step": round(t / ms_step, 3)}
         if ln:
@@ -309,7 +333,10 @@ def run_gpu_arm(args):
             ach = by / (t * 1e-3) / 1e9
             roof_hbm = {"bound": "hbm", "kernel": "ln_fwd_kernel/ln_bwd_kernel (fused residual-add + LayerNorm)",
                         "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4),
-                        "traffic": None, "peak_source": pk["src"], "launches_per_step": len(ln),
+                        "traffic": traffic("ln_kernel"),
+                        "traffic_unit": "DRAM bytes per launch (ncu, mean over ln_fwd/ln_bwd launches; profiles/traffic.json)",
+                        "algorithmic_bytes_per_launch": round(by / len(ln)),
+                        "peak_source": pk["src"], "launches_per_step": len(ln),
                         "ms_per_step_in_kernel": round(t, 3)}
 
     if rank == 0:
