@@ -5,18 +5,19 @@
 // ssl/dino/head.py:10-17):
 //   forward   C[M,N]  = A[M,K] * W[N,K]^T      (both operands K-major)
 //   dgrad     dX[M,K] = dY[M,N] * W[N,K]       (B operand MN-major)
-//   wgrad     dW[N,K] = dY[M,N]^T * X[M,K]     (both operands MN-major, split-K + fp32 red)
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner,
-// warps 2-9 = epilogue (two per TMEM lane quadrant, half of the tile's columns each, so every
-// SM sub-partition has two warps to hide the epilogue's arithmetic latency). Accumulators are
-// double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1. Each epilogue
-// warp drains its 32 rows in 32-column chunks: tcgen05.ld (software-pipelined one chunk ahead) -> bias / GELU /
-// dGELU / dropout in registers -> 16-byte st.shared into a private, double-buffered staging tile
-// laid out in the TMA swizzle (bank-conflict free) -> one elected lane issues the bulk tensor
-// store, so global writes are full 64/128-byte row segments instead of per-thread row fragments.
-// The dGELU epilogue's pre-activation tile arrives the same way in reverse (TMA load, one chunk
-// ahead). Tiles whose output cannot be a TMA target (row pitch not a multiple of 16 bytes) and
-// split-K partial sums use the direct register->global epilogue.
+//   wgrad     dW[N,K] = dY[M,N]^T * X[M,K]     (both operands MN-major, split-K + TMA reduce-add)
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner,
+// warps 2-17 = epilogue (four per TMEM lane quadrant; the tile's 32-column chunks are dealt
+// round-robin, so every SM sub-partition has four warps to hide the epilogue's arithmetic
+// latency). Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of
+// tile i+1. Each epilogue warp drains its 32 rows one 32-column chunk at a time: tcgen05.ld ->
+// bias / GELU / dGELU / dropout in registers -> 16-byte st.shared into a private 4 KB staging tile
+// laid out in the TMA swizzle (bank-conflict free) -> one lane issues the bulk tensor store, so
+// global writes are full 64/128-byte row segments instead of per-thread row fragments. Split-K
+// partial sums leave the same way as TMA reduce-adds. The dGELU epilogue reads its saved
+// pre-activations straight from global memory (64 contiguous bytes per thread). Tiles whose
+// output cannot be a TMA target (row pitch not a multiple of 16 bytes) use the direct
+// register->global epilogue.
 #include <stdlib.h>
 #include <string.h>
 
@@ -824,6 +825,11 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   }
 
   int bn = pick_block_n((int)N);
+  {
+    // experiment hook: VITSSL_GEMM_BN=<n> forces the tile width when it divides N (64/128/192/256)
+    static const int bn_env = getenv("VITSSL_GEMM_BN") ? atoi(getenv("VITSSL_GEMM_BN")) : 0;
+    if (bn_env > 0 && N % bn_env == 0 && (bn_env == 64 || bn_env == 128 || bn_env == 192 || bn_env == 256)) bn = bn_env;
+  }
   // CTA pairs (cta_group::2) for the compute-bound GEMMs: 256-row tiles, B columns split across
   // the pair. Measured on B200: +12..19 % where both N and K are large (8192^3: 1162 -> 1388 TF/s,
   // ViT-B shapes 1240-1360 TF/s = cuBLAS parity); no gain on ViT-S shapes (N or K = 384), which are
