@@ -153,6 +153,11 @@ typedef struct {
   float* const* dwqkv; float* const* dwo; float* const* dw1; float* const* db1;
   float* const* dw2; float* const* db2;
   float* const* dg1; float* const* dbe1; float* const* dg2; float* const* dbe2;
+  /* layer range of this call: blocks l_end-1 ... l_begin (l_end = 0 means L). A caller may split the
+   * backward into several calls, highest layers first, with the same scratch buffers (they carry
+   * the state between calls) — e.g. to start reducing a chunk's gradients across ranks while the
+   * next chunk is computed. */
+  int64_t l_begin, l_end;
 } vitssl_encoder_bwd_args;
 int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* args, vitssl_stream_t stream);
 

@@ -57,6 +57,42 @@ def _worker(rank, world, port, q):
             assert torch.allclose(a, b, atol=1e-6), (a - b).abs().max()
         assert frozen.grad is None
 
+        # gradients averaged INSIDE an autograd node (the encoder stack's chunked backward): the
+        # node hands its flat gradient buffer to prereduce() and the hooks must not reduce the
+        # same parameters again; a second use of the same parameters in the graph accumulates
+        class _Scaled(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, w, b):
+                ctx.save_for_backward(x, w)
+                ctx.params = (w, b)
+                return x @ w.t() + b
+
+            @staticmethod
+            def backward(ctx, gy):
+                x, w = ctx.saved_tensors
+                flat = torch.cat([(gy.t() @ x).reshape(-1), gy.sum(0)])
+                s_ = dp.sync_for(ctx.params)
+                assert s_ is sync2
+                s_.prereduce(flat, ctx.params)
+                s_.join()
+                return gy @ w, flat[:w.numel()].view_as(w), flat[w.numel():]
+
+        lin = torch.nn.Linear(16, 8)
+        tail = torch.nn.Linear(8, 8)
+        both = torch.nn.ModuleList([lin, tail])
+        sync2 = dp.attach(both, bucket_bytes=256)
+        for _ in range(2):
+            both.zero_grad(set_to_none=True)
+            y = _Scaled.apply(xs, lin.weight, lin.bias) + _Scaled.apply(2 * xs, lin.weight, lin.bias)
+            ((tail(y) - ys) ** 2).mean().backward()
+        ref_lin, ref_tail = torch.nn.Linear(16, 8), torch.nn.Linear(8, 8)
+        ref_lin.load_state_dict(lin.state_dict()); ref_tail.load_state_dict(tail.state_dict())
+        ((ref_tail(ref_lin(X) + ref_lin(2 * X)) - Y) ** 2).mean().backward()
+        for a, b in zip([lin.weight.grad, lin.bias.grad, tail.weight.grad, tail.bias.grad],
+                        [ref_lin.weight.grad, ref_lin.bias.grad, ref_tail.weight.grad, ref_tail.bias.grad]):
+            assert torch.allclose(a, b, atol=1e-5), (a - b).abs().max()
+        assert not sync2.prereduced  # cleared by the end-of-backward callback
+
         # center-style sum
         t = torch.full((5,), float(rank + 1))
         dp.all_reduce_sum_(t)

@@ -350,3 +350,45 @@ def test_encoder_stack_c_sequencer_matches_per_op_path(monkeypatch):
         assert torch.equal(o1, o2) and torch.equal(pr1, pr2), (train, p)
         for a, b in zip(g1, g2):   # split-K wgrad accumulates with fp32 atomics: order-dependent last bits
             assert (a - b).abs().max().item() <= 1e-5 * max(b.abs().max().item(), 1e-6), (train, p)
+
+
+def test_encoder_stack_chunked_backward_matches_single_call(monkeypatch):
+    """Under data parallelism the stack backward runs as layer chunks (csrc/encoder.cu layer ranges)
+    and hands each chunk's contiguous gradient slice to GradSync.prereduce before the next chunk
+    starts. With a stand-in sync object the chunked path must reproduce the single-call gradients,
+    and every parameter of the stack must be covered by exactly one slice."""
+    from vit_core import EncoderBlock
+    from vit_core._backend import functional as Fb
+    torch.manual_seed(11)
+    L = 5
+    blocks = torch.nn.ModuleList([EncoderBlock(128, 2, 256, 0.1) for _ in range(L)]).cuda().train()
+    x = torch.randn(3, 50, 128, device="cuda")
+    monkeypatch.setattr(Fb, "_new_seed", lambda: 99)
+
+    def run():
+        blocks.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        out = Fb.encoder_stack(blocks, xi)
+        out = out[0] if isinstance(out, tuple) else out
+        (out.square().mean() + out.sum() * 1e-3).backward()
+        return [p_.grad.clone() for p_ in blocks.parameters()] + [xi.grad.clone()]
+
+    ref = run()
+    seen = []
+
+    class FakeSync:
+        def prereduce(self, flat, params):
+            assert flat.is_contiguous() and flat.dtype == torch.float32
+            params = list(params)
+            assert flat.numel() == sum(p_.numel() for p_ in params)
+            seen.extend(id(p_) for p_ in params)
+
+        def join(self):
+            pass
+
+    monkeypatch.setattr(Fb.dp, "sync_for", lambda params: FakeSync())
+    got = run()
+    assert sorted(seen) == sorted(id(p_) for p_ in blocks.parameters())
+    assert len(ref) == len(got)
+    for a, b in zip(got, ref):
+        assert (a - b).abs().max().item() <= 1e-5 * max(b.abs().max().item(), 1e-6)

@@ -70,11 +70,19 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
   const int64_t M = B * S;
   const float p = f->dropout_p;
   const float scale = 0.125f;
-  // gradient of the final add: the stream gradient passes through, the branch gets mask/(1-p) * g
-  VITSSL_TRY(vitssl_add_layernorm_bwd_acc(nullptr, nullptr, 0, nullptr, nullptr, nullptr, a->gout, D, nullptr, 0,
-                                      a->dbranch, nullptr, nullptr, M, D, p, f->seed, (uint64_t)(3 * L - 1), stream));
-  const float* gs = a->gout;  // gradient on the residual stream
-  for (int64_t l = L - 1; l >= 0; --l) {
+  const int64_t l_hi = a->l_end > 0 ? a->l_end : L, l_lo = a->l_begin;
+  VITSSL_REQUIRE(0 <= l_lo && l_lo < l_hi && l_hi <= L, VITSSL_ERR_ARG, "encoder_stack_bwd: bad layer range [%lld, %lld)",
+                 (long long)l_lo, (long long)l_hi);
+  const float* gs;  // gradient on the residual stream
+  if (l_hi == L) {
+    // gradient of the final add: the stream gradient passes through, the branch gets mask/(1-p) * g
+    VITSSL_TRY(vitssl_add_layernorm_bwd_acc(nullptr, nullptr, 0, nullptr, nullptr, nullptr, a->gout, D, nullptr, 0,
+                                            a->dbranch, nullptr, nullptr, M, D, p, f->seed, (uint64_t)(3 * L - 1), stream));
+    gs = a->gout;
+  } else {
+    gs = a->gs[1];  // left there (with dbranch) by the previous call
+  }
+  for (int64_t l = l_hi - 1; l >= l_lo; --l) {
     const void* dy2 = a->dbranch;
     // FFN backward
     VITSSL_TRY(vitssl_gemm_bf16(dy2, f->w2[l], a->du, M, F, D, D, F, F, 0, 1, VITSSL_EPI_DGELU, nullptr, f->u[l], F,

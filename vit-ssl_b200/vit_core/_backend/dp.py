@@ -24,6 +24,7 @@ from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
 from torch.autograd import Variable
 
 DEFAULT_BUCKET_BYTES = 32 << 20
+_SYNCS: "weakref.WeakSet" = weakref.WeakSet()  # live GradSync objects (sync_for looks a parameter up here)
 
 
 def world_size() -> int:
@@ -85,7 +86,9 @@ class GradSync:
         self.comm_stream = None
         self.handles = []
         self.reduced_bytes = 0
+        self.prereduced = set()  # ids of parameters whose gradient was averaged inside backward already
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook()) for p in params]
+        _SYNCS.add(self)
 
     def _make_hook(self):
         ref = weakref.ref(self)
@@ -109,8 +112,42 @@ class GradSync:
         if self.ready[bi] == len(self.buckets[bi]):
             self._launch(bi)
 
+    def prereduce(self, flat: torch.Tensor, params: Iterable[torch.Tensor]) -> None:
+        """Average `flat` (a contiguous buffer holding the gradient contributions that an autograd
+        node is about to return for `params`) across ranks, in place, asynchronously on the
+        communication stream — called from inside that node's backward so the all-reduce overlaps
+        the rest of the backward pass (the encoder stack is ONE node: without this its gradients,
+        98 % of the model, would only become visible to the hooks when the whole stack is done).
+        The hooks then skip these parameters. Linear, so it composes with gradient accumulation
+        from several nodes (DINO's global and local passes share parameters)."""
+        if self.world <= 1:
+            return
+        self.reduced_bytes += flat.numel() * flat.element_size()
+        if not self.callback_queued:
+            Variable._execution_engine.queue_callback(self._finalize)
+            self.callback_queued = True
+        if flat.is_cuda:
+            if self.comm_stream is None:
+                self.comm_stream = torch.cuda.Stream()
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                flat.div_(self.world)
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                flat.record_stream(self.comm_stream)
+        else:
+            flat.div_(self.world)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        for p in params:
+            self.prereduced.add(id(p))
+
+    def join(self) -> None:
+        """Make the current stream wait for the reductions issued so far (the autograd engine is
+        about to read / accumulate the tensors `prereduce` is averaging in place)."""
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
     def _launch(self, bi: int) -> None:
-        grads = [p.grad for p in self.buckets[bi] if p.grad is not None]
+        grads = [p.grad for p in self.buckets[bi] if p.grad is not None and id(p) not in self.prereduced]
         self.launched[bi] = True
         if not grads:
             return
@@ -151,11 +188,25 @@ class GradSync:
         self.ready = [0] * len(self.buckets)
         self.launched = [False] * len(self.buckets)
         self.callback_queued = False
+        self.prereduced.clear()
 
     def remove(self) -> None:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+
+
+def sync_for(params: Iterable[torch.Tensor]):
+    """The live GradSync that owns (all of) the trainable tensors in `params`, or None."""
+    if not is_distributed():
+        return None
+    ids = [id(p) for p in params if getattr(p, "requires_grad", False)]
+    if not ids:
+        return None
+    for s in list(_SYNCS):
+        if s._hooks and all(i in s.bucket_of for i in ids):
+            return s
+    return None
 
 
 def attach(module: torch.nn.Module, bucket_bytes: int = DEFAULT_BUCKET_BYTES, broadcast: bool = True):

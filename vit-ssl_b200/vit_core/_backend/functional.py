@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from . import ops
+from . import dp, ops
 from .ops import EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_NONE
 
 
@@ -128,6 +128,9 @@ def attention_probs(q, k, H):
 # params per block (12): wq wk wv wo | w1 b1 w2 b2 | g1 be1 g2 be2
 # dropout sites per block l: 3l (after out-proj), 3l+1 (after GELU), 3l+2 (after FFN)
 # ----------------------------------------------------------------------------------------
+DP_STACK_CHUNKS = 4  # layer chunks of the stack backward under data parallelism (3 layers each for L = 12)
+
+
 class _EncoderStackFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, meta, *params):
@@ -203,7 +206,15 @@ class _EncoderStackFn(torch.autograd.Function):
             st, ctx.stack_state = ctx.stack_state, None
             L = ctx.meta.L
             D = ctx.shape[2]
-            dx, gr = ops.encoder_stack_bwd(st, g)
+            # data parallel: the stack runs as a few layer chunks, and each chunk's gradient slice
+            # starts its all-reduce on the communication stream while the next chunk computes
+            sync = dp.sync_for(ctx.params) if all(ctx.needs_input_grad[2:]) else None
+            if sync is not None:
+                dx, gr = ops.encoder_stack_bwd(st, g, n_chunks=min(L, DP_STACK_CHUNKS),
+                                               on_chunk=lambda flat, lo, hi: sync.prereduce(flat, ctx.params[12 * lo:12 * hi]))
+                sync.join()  # only the last chunk's all-reduce is still in flight here
+            else:
+                dx, gr = ops.encoder_stack_bwd(st, g)
             grads = []
             for l in range(L):
                 wq = gr["dwqkv"][l]

@@ -468,7 +468,8 @@ class _EncBwdArgs(_ct.Structure):
     _fields_ = ([("fwd", _ct.POINTER(_EncFwdArgs)), ("gout", _ct.c_void_p), ("dx", _ct.c_void_p)]
                 + [(n, _ct.c_void_p) for n in ("dbranch", "du", "dxn", "dctx", "dqkv")]
                 + [("gs", _ct.c_void_p * 2)]
-                + [(n, _PP) for n in ("dwqkv", "dwo", "dw1", "db1", "dw2", "db2", "dg1", "dbe1", "dg2", "dbe2")])
+                + [(n, _PP) for n in ("dwqkv", "dwo", "dw1", "db1", "dw2", "db2", "dg1", "dbe1", "dg2", "dbe2")]
+                + [("l_begin", _ct.c_int64), ("l_end", _ct.c_int64)])
 
 
 def _layer_ptrs(t, L, per_layer=True):
@@ -550,8 +551,13 @@ def encoder_stack_last_qkv(st):
     return qkv[qkv.shape[0] - 1].view(B, S, 3 * D)
 
 
-def encoder_stack_bwd(st, gout):
-    """gout fp32 [B,S,D] contiguous -> (dx fp32 [B,S,D], per-layer gradient tensors dict)."""
+def encoder_stack_bwd(st, gout, n_chunks=1, on_chunk=None):
+    """gout fp32 [B,S,D] contiguous -> (dx fp32 [B,S,D], per-layer gradient views dict name -> list of L).
+
+    The backward may run as `n_chunks` C calls over descending layer ranges; after each one
+    `on_chunk(flat_slice, l_lo, l_hi)` is called with the contiguous fp32 slice that holds every
+    parameter gradient of those layers (data parallelism starts their all-reduce there, while the
+    next chunk computes)."""
     B, S, D, H, F_, L = st.dims
     M = B * S
     dev = gout.device
@@ -561,25 +567,34 @@ def encoder_stack_bwd(st, gout):
     du = torch.empty((M, F_), device=dev, dtype=bf)
     dqkv = torch.empty((M, 3 * D), device=dev, dtype=bf)
     gs = torch.empty((2, M, D), device=dev, dtype=f32)
-    # every parameter gradient of the stack lives in ONE zeroed fp32 buffer: the C side accumulates
-    # into it (split-K TMA reduce-adds, column sums, LayerNorm dgamma/dbeta), so a single fill
-    # replaces ~125 per-kernel memsets per step
-    shapes = {"dwqkv": (L, 3 * D, D), "dwo": (L, D, D), "dw1": (L, F_, D), "db1": (L, F_), "dw2": (L, D, F_),
-              "db2": (L, D), "dg1": (L, D), "dbe1": (L, D), "dg2": (L, D), "dbe2": (L, D)}
-    sizes = {k: int(torch.Size(v).numel()) for k, v in shapes.items()}
-    flat = torch.zeros((sum(sizes.values()),), device=dev, dtype=f32)
-    g, off = {}, 0
-    for k, shp in shapes.items():
-        g[k] = flat[off:off + sizes[k]].view(shp)
-        off += sizes[k]
+    # every parameter gradient of the stack lives in ONE zeroed fp32 buffer, layer-major: the C side
+    # accumulates into it (split-K TMA reduce-adds, column sums, LayerNorm dgamma/dbeta), so a
+    # single fill replaces ~125 per-kernel memsets per step, and a range of layers is one slice
+    shapes = (("dwqkv", (3 * D, D)), ("dwo", (D, D)), ("dw1", (F_, D)), ("db1", (F_,)), ("dw2", (D, F_)),
+              ("db2", (D,)), ("dg1", (D,)), ("dbe1", (D,)), ("dg2", (D,)), ("dbe2", (D,)))
+    per_layer = sum(int(torch.Size(shp).numel()) for _, shp in shapes)
+    flat = torch.zeros((L * per_layer,), device=dev, dtype=f32)
+    g = {k: [] for k, _ in shapes}
+    for l in range(L):
+        off = l * per_layer
+        for k, shp in shapes:
+            n = int(torch.Size(shp).numel())
+            g[k].append(flat[off:off + n].view(shp))
+            off += n
     b = _EncBwdArgs()
     b.fwd = _ct.pointer(st.args)
     b.gout, b.dx = _p(gout), _p(dx)
     b.dbranch, b.dxn, b.dctx = _p(tmp_d[0]), _p(tmp_d[1]), _p(tmp_d[2])
     b.du, b.dqkv = _p(du), _p(dqkv)
     b.gs[0], b.gs[1] = _p(gs[0]), _p(gs[1])
-    arrays = {name: _layer_ptrs(t, L) for name, t in g.items()}
+    arrays = {name: (_ct.c_void_p * L)(*[_p(t) for t in views]) for name, views in g.items()}
     for name, arr in arrays.items():
         setattr(b, name, _ct.cast(arr, _PP))
-    _l.call("vitssl_encoder_stack_bwd", _ct.addressof(b), _l.stream_ptr())
+    n_chunks = max(1, min(int(n_chunks), L))
+    bounds = [round(i * L / n_chunks) for i in range(n_chunks + 1)]
+    for c in reversed(range(n_chunks)):
+        b.l_begin, b.l_end = bounds[c], bounds[c + 1]
+        _l.call("vitssl_encoder_stack_bwd", _ct.addressof(b), _l.stream_ptr())
+        if on_chunk is not None:
+            on_chunk(flat[bounds[c] * per_layer:bounds[c + 1] * per_layer], bounds[c], bounds[c + 1])
     return dx, g
