@@ -61,6 +61,17 @@ int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N
                      int split_k, float dropout_p, uint64_t philox_seed, uint64_t philox_offset,
                      vitssl_stream_t stream);
 
+/* fp32 C = alpha * op(A) op(B) as above (epilogue NONE) and, fused into the same kernel,
+ * a_rowsum[m] += alpha * sum_k op(A)[m, k]: with A = dY^T (a_mn = 1) this is the bias gradient of
+ * the Linear whose weight gradient the GEMM computes (feed_forward.py:26,28), obtained as one extra
+ * 16-column tcgen05.mma per k-step against a constant all-ones operand instead of a separate pass
+ * over dY. a_rowsum (fp32 [M]) is ACCUMULATED into: the caller zeroes it. Returns VITSSL_ERR_SHAPE
+ * for configurations it does not cover (CTA-pair shapes, unaligned operands); callers then fall
+ * back to vitssl_gemm_bf16 + vitssl_colsum_bf16. split_k as for vitssl_gemm_bf16. */
+int vitssl_gemm_bf16_rowsum(const void* A, const void* B, void* C, float* a_rowsum, int64_t M,
+                            int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn,
+                            int b_mn, float alpha, int split_k, vitssl_stream_t stream);
+
 /* ---- fused residual-add (+dropout) + LayerNorm ------------------------------------------
  * encoder_block.py:40-52:  x_out = x + dropout(branch);  y = LayerNorm(x_out) (eps, affine).
  *   x      fp32 rows of pitch ldx (elements);  branch bf16 dense [rows,D] or NULL (then x_out

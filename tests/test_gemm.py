@@ -172,3 +172,23 @@ def test_gemm_cta_pair_mode_epilogues(M, N, K):
     for split in (0, -1, 3):
         dw = ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=split)
         assert _err(dw, g.double().t() @ x.double()) < 2e-5, split
+
+
+@pytest.mark.parametrize("Mtok,Nout,Kin", [(4096, 384, 1536), (4096, 1536, 384), (1000, 200, 512), (777, 64, 64), (2048, 128, 256)])
+def test_gemm_rowsum_fuses_the_bias_gradient(Mtok, Nout, Kin):
+    """dW[Nout, Kin] = dY^T X and db[Nout] = colsum(dY) from one kernel (ones-operand MMA into a
+    spare TMEM accumulator): split-K variants, ragged row tiles, accumulation into caller buffers."""
+    ops = _ops()
+    dy, x = _mk((Mtok, Nout), 31), _mk((Mtok, Kin), 32)
+    dw_ref = dy.double().t() @ x.double()
+    db_ref = dy.double().sum(0)
+    for split in (0, -1, 3):
+        dw, db = ops.gemm_rowsum(dy, x, a_mn=True, b_mn=True, split_k=split)
+        assert _err(dw, dw_ref) < 2e-5, split
+        assert _err(db, db_ref) < 2e-5, split
+    # accumulate into caller-zeroed buffers (the encoder backward's mode), twice -> 2x
+    dw = torch.zeros((Nout, Kin), device="cuda"); db = torch.zeros((Nout,), device="cuda")
+    if Mtok >= 1024:  # split_k = -2 accumulates only when the problem is actually split
+        for _ in range(2):
+            ops.gemm_rowsum(dy, x, a_mn=True, b_mn=True, split_k=-2, out=dw, rowsum=db)
+        assert _err(db, 2 * db_ref) < 2e-5

@@ -87,14 +87,20 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
     // FFN backward
     VITSSL_TRY(vitssl_gemm_bf16(dy2, f->w2[l], a->du, M, F, D, D, F, F, 0, 1, VITSSL_EPI_DGELU, nullptr, f->u[l], F,
                                 1.0f, 0, 0, p, f->seed, (uint64_t)(3 * l + 1), stream));
-    VITSSL_TRY(vitssl_gemm_bf16(dy2, f->h[l], a->dw2[l], D, F, M, D, F, F, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
-                                1.0f, 1, -2, 0.f, 0, 0, stream));
-    VITSSL_TRY(vitssl_colsum_bf16_acc(dy2, D, M, D, a->db2[l], stream));
+    // dW2 = dy2^T h with db2 = colsum(dy2) from the same kernel (ones-operand MMA); shapes the fused
+    // form does not cover (CTA pairs) fall back to GEMM + column-sum pass
+    if (vitssl_gemm_bf16_rowsum(dy2, f->h[l], a->dw2[l], a->db2[l], D, F, M, D, F, F, 1, 1, 1.0f, -2, stream) != 0) {
+      VITSSL_TRY(vitssl_gemm_bf16(dy2, f->h[l], a->dw2[l], D, F, M, D, F, F, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
+                                  1.0f, 1, -2, 0.f, 0, 0, stream));
+      VITSSL_TRY(vitssl_colsum_bf16_acc(dy2, D, M, D, a->db2[l], stream));
+    }
     VITSSL_TRY(vitssl_gemm_bf16(a->du, f->w1[l], a->dxn, M, D, F, F, D, D, 0, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
                                 1.0f, 0, 0, 0.f, 0, 0, stream));
-    VITSSL_TRY(vitssl_gemm_bf16(a->du, f->xn2[l], a->dw1[l], F, D, M, F, D, D, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr,
-                                0, 1.0f, 1, -2, 0.f, 0, 0, stream));
-    VITSSL_TRY(vitssl_colsum_bf16_acc(a->du, F, M, F, a->db1[l], stream));
+    if (vitssl_gemm_bf16_rowsum(a->du, f->xn2[l], a->dw1[l], a->db1[l], F, D, M, F, D, D, 1, 1, 1.0f, -2, stream) != 0) {
+      VITSSL_TRY(vitssl_gemm_bf16(a->du, f->xn2[l], a->dw1[l], F, D, M, F, D, D, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr,
+                                  0, 1.0f, 1, -2, 0.f, 0, 0, stream));
+      VITSSL_TRY(vitssl_colsum_bf16_acc(a->du, F, M, F, a->db1[l], stream));
+    }
     // LN2 + residual: gs <- d(xmid), dy1 = dropout-masked gradient of the attention branch
     float* gs_mid = a->gs[0];
     VITSSL_TRY(vitssl_add_layernorm_bwd_acc(a->dxn, f->xmid[l], D, f->mean2[l], f->rstd2[l], f->g2[l], gs, D, gs_mid, D,

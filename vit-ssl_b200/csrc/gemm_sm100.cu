@@ -58,7 +58,9 @@ struct GemmEpi {
   uint32_t drop_th2;  // (p * 32768) * 0x10001, 0 = no dropout (common.cuh: dropout_lane_mask2)
   float drop_scale;
   PhiloxKeys7 keys;  // dropout generator state: (seed, offset) expanded to round keys on the host
+  float* a_colsum;   // nullable: a_colsum[m] += alpha * sum_k op(A)[m, k] (bias gradient fused into a wgrad)
 };
+constexpr int ONES_OFFSET = 512;  // all-ones bf16 block (512 B) inside the 1 KB barrier page
 
 // PAIR = true: two CTAs of a cluster share one 256 x BN tile (tcgen05 cta_group::2): each CTA
 // stages its own 128 rows of A but only BN/2 columns of B, so the shared-memory fill and the
@@ -287,6 +289,16 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
     __syncwarp();
+    if constexpr (OUT_F32 && MODE == VITSSL_EPI_NONE) {
+      // fused row sums of op(A) (the tile's extra 16-column accumulator, all columns equal):
+      // one warp per lane quadrant adds its 32 rows' partial sums
+      if (e.a_colsum != nullptr && n_blk == 0 && cg == 0) {
+        const uint32_t v = tmem_ld_32x1(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN + acc * 16);
+        tmem_ld_wait();
+        if (row0 + lane < s.M) atomicAdd(e.a_colsum + row0 + lane, __uint_as_float(v) * e.alpha);
+        __syncwarp();
+      }
+    }
     if (cg >= nch) {
       tc_fence_before();
       if (lane == 0) tempty_arrive(tc, acc);
@@ -476,6 +488,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if constexpr (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
     else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
+  if (warp == 2 && e.a_colsum != nullptr) {  // 512 bytes of bf16 1.0 for the row-sum MMA's B operand
+    reinterpret_cast<uint4*>(smem_al + ONES_OFFSET)[lane] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all();  // the peer's barriers exist before anything signals them
   else __syncthreads();
@@ -545,43 +561,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0 && rank == 0) {
+    // The whole warp walks the tile / k-block schedule and the barrier waits (uniform control
+    // flow); one elected lane issues the MMAs and commits. Descriptor low words are derived from
+    // the stage base with one add per k-step and every form shares the high word, so an MMA costs a
+    // few uniform-datapath instructions. (Issued from `if (lane == 0)` the same code needed a
+    // vector->uniform hand-off loop per operand: ~18 instructions per MMA against a 96-cycle MMA at
+    // BN = 192 — the issuer, not the tensor pipe, paced the small-tile GEMMs.)
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      constexpr uint32_t HI = 0x40004040u;  // SBO 1024 | descriptor version 1 | SWIZZLE_128B
+      constexpr uint32_t LBO_K = (16u >> 4) << 16, LBO_MN = (8192u >> 4) << 16;
+      constexpr uint32_t A_STEP = A_MN ? (2048u >> 4) : (32u >> 4), B_STEP = B_MN ? (2048u >> 4) : (32u >> 4);
+      const uint32_t ring_lo = smem_u32(smem) >> 4;
+      // fused row sums: D1[128 x 16] += A_tile * ones, issued for the first column tile of every row tile
+      constexpr uint32_t IDESC_ONES = umma_idesc_bf16(BLOCK_M, 16, A_MN, false);
+      constexpr uint32_t HI_ONES = (256u >> 4) | (1u << 14);  // SBO 256, version 1, no swizzle
+      const uint32_t ones_lo = (smem_u32(smem_al + ONES_OFFSET) >> 4) | ((128u >> 4) << 16);
       for (int w = tc.worker; w < num_work; w += tc.nworkers) {
         const int sp = w / (s.n_tiles * s.m_tiles);
         const int kb0 = sp * s.kblocks_per_split;
         const int kb1 = min(kb0 + s.kblocks_per_split, s.kblocks_total);
+        const bool row_sums = !PAIR && e.a_colsum != nullptr && (w % s.n_tiles) == 0;
         mbar_wait_parked(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_parked(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t b_base = a_base + A_TILE_BYTES;
+          const uint32_t a_lo = (ring_lo + stage * (STAGE_BYTES >> 4)) | (A_MN ? LBO_MN : LBO_K);
+          const uint32_t b_lo = (ring_lo + stage * (STAGE_BYTES >> 4) + (A_TILE_BYTES >> 4)) | (B_MN ? LBO_MN : LBO_K);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // K-major: 16 bf16 = 32 bytes along the swizzled row; 8-row groups 1024 B apart.
-            // MN-major: 16 k-rows = 2048 bytes; 64-wide MN groups 8192 B apart (LBO),
-            //           8-row k groups 1024 B apart (SBO).
-            const uint64_t da = A_MN ? umma_desc_sw128(a_base + k * 2048, 8192, 1024)
-                                     : umma_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? umma_desc_sw128(b_base + k * 2048, 8192, 1024)
-                                     : umma_desc_sw128(b_base + k * 32, 16, 1024);
-            if constexpr (PAIR) umma_bf16_ss_pair(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16_ss(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // K-major: 16 bf16 = 32 bytes along the swizzled row; 8-row groups 1024 B apart.
+              // MN-major: 16 k-rows = 2048 bytes; 64-wide MN groups 8192 B apart (LBO),
+              //           8-row k groups 1024 B apart (SBO).
+              umma_bf16_ss_lo<PAIR>(d_tmem, a_lo + k * A_STEP, b_lo + k * B_STEP, HI, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (row_sums) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k)
+                umma_bf16_ss_lohi(tmem_base + 2 * BN + acc * 16, a_lo + k * A_STEP, HI, ones_lo, HI_ONES, IDESC_ONES,
+                                  (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+            if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);
           }
-          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
-          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc]);
-        else umma_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc]);
+          else umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -777,12 +815,12 @@ int pick_block_n(int N) {
 
 using namespace vitssl;
 
-extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N,
-                                int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn,
-                                int b_mn, int epilogue, const float* bias, void* aux,
-                                int64_t ld_aux, float alpha, int out_fp32, int split_k,
-                                float dropout_p, uint64_t philox_seed, uint64_t philox_offset,
-                                cudaStream_t stream) {
+static int gemm_impl(const void* A, const void* B, void* C, int64_t M, int64_t N,
+                     int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn,
+                     int b_mn, int epilogue, const float* bias, void* aux,
+                     int64_t ld_aux, float alpha, int out_fp32, int split_k,
+                     float dropout_p, uint64_t philox_seed, uint64_t philox_offset, float* a_colsum,
+                     cudaStream_t stream) {
   VITSSL_REQUIRE(A && B && C, VITSSL_ERR_ARG, "gemm: null operand");
   VITSSL_REQUIRE(M > 0 && N > 0 && K > 0, VITSSL_ERR_SHAPE, "gemm: empty problem %lld x %lld x %lld",
                  (long long)M, (long long)N, (long long)K);
@@ -804,6 +842,7 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   e.drop_th2 = static_cast<uint32_t>(dropout_p * 32768.0f) * 0x10001u;
   e.drop_scale = 1.0f / (1.0f - dropout_p);
   e.keys = make_philox_keys7(philox_seed, philox_offset);
+  e.a_colsum = a_colsum;
 
   // TMA needs 16-byte aligned bases and row pitches
   const bool tma_ok = (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
@@ -816,6 +855,7 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
     out_ok = out_ok && !out_fp32 && (reinterpret_cast<uintptr_t>(aux) % 16 == 0) && (ld_aux % 8 == 0);
   if (!tma_ok || (gelu_mode && !out_ok)) {
     VITSSL_REQUIRE(dropout_p == 0.f, VITSSL_ERR_SHAPE, "gemm: dropout unsupported on unaligned path");
+    VITSSL_REQUIRE(a_colsum == nullptr, VITSSL_ERR_SHAPE, "gemm_rowsum: unaligned operands");
     e.atomic = 0; e.vec_ok = 0; e.tma_out = 0;
     dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + 31) / 32));
     gemm_simt_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A),
@@ -841,6 +881,12 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   if (pair) {
     if (bn == 64) pair = false;
     if (b_mn && bn == 192) bn = 128;
+  }
+  if (a_colsum != nullptr) {
+    // fused row sums need 32 spare TMEM columns (BN <= 192), the staged fp32 epilogue and a single CTA per tile
+    if (bn == 256) bn = (N % 192 == 0) ? 192 : 128;
+    VITSSL_REQUIRE(!pair && out_ok && out_fp32 && epilogue == VITSSL_EPI_NONE && 2 * bn + 32 <= 512, VITSSL_ERR_SHAPE,
+                   "gemm_rowsum: configuration not supported (CTA-pair shape, bf16 output or unaligned C)");
   }
   const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
   GemmShape s{};
@@ -899,4 +945,22 @@ extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M
   if (!a_mn && b_mn) return dispatch_bn<false, true>(bn, pair, ta, tb, tc, tx, s, e, stream);
   if (a_mn && b_mn) return dispatch_bn<true, true>(bn, pair, ta, tb, tc, tx, s, e, stream);
   return dispatch_bn<true, false>(bn, pair, ta, tb, tc, tx, s, e, stream);
+}
+
+extern "C" int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N,
+                                int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn,
+                                int b_mn, int epilogue, const float* bias, void* aux,
+                                int64_t ld_aux, float alpha, int out_fp32, int split_k,
+                                float dropout_p, uint64_t philox_seed, uint64_t philox_offset,
+                                cudaStream_t stream) {
+  return gemm_impl(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, bias, aux, ld_aux, alpha, out_fp32, split_k,
+                   dropout_p, philox_seed, philox_offset, nullptr, stream);
+}
+
+extern "C" int vitssl_gemm_bf16_rowsum(const void* A, const void* B, void* C, float* a_rowsum, int64_t M, int64_t N,
+                                       int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn, int b_mn,
+                                       float alpha, int split_k, cudaStream_t stream) {
+  VITSSL_REQUIRE(a_rowsum != nullptr, VITSSL_ERR_ARG, "gemm_rowsum: null a_rowsum");
+  return gemm_impl(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, VITSSL_EPI_NONE, nullptr, nullptr, 0, alpha, 1, split_k,
+                   0.f, 0, 0, a_rowsum, stream);
 }

@@ -11,7 +11,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))  # .../vit-ssl_b200
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libvitssl_b200.so")
+# VITSSL_LIB points at an alternative build of the same library (A/B timing of two builds on one box)
+LIB_PATH = os.environ.get("VITSSL_LIB") or os.path.join(_PKG_ROOT, "lib", "libvitssl_b200.so")
 
 _T = {
     "p": ctypes.c_void_p,
@@ -28,6 +29,7 @@ SIGNATURES = {}
 # ld_aux | alpha | out_fp32, split_k | dropout_p | seed, offset | stream)
 SIGNATURES["vitssl_gemm_bf16"] = "ppp" + "llllll" + "iii" + "pp" + "l" + "f" + "ii" + "f" + "uu" + "s"
 
+SIGNATURES["vitssl_gemm_bf16_rowsum"] = "pppp" + "llllll" + "ii" + "f" + "i" + "s"
 SIGNATURES["vitssl_add_layernorm_fwd"] = "plpp" + "pp" + "ppp" + "ll" + "ff" + "uu" + "s"
 SIGNATURES["vitssl_add_layernorm_bwd"] = "ppl" + "ppp" + "pl" + "pl" + "p" + "pp" + "ll" + "f" + "uu" + "s"
 SIGNATURES["vitssl_add_layernorm_bwd_acc"] = SIGNATURES["vitssl_add_layernorm_bwd"]
@@ -86,6 +88,8 @@ def _load():
     lib.vitssl_randperm_offset_per_call.restype = ctypes.c_int64
     lib.vitssl_randperm_offset_per_call.argtypes = [ctypes.c_int64]
     for name, sig in SIGNATURES.items():
+        if os.environ.get("VITSSL_LIB") and not hasattr(lib, name):
+            continue  # an older build given for A/B timing may predate an entry point
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [_T[c] for c in sig]

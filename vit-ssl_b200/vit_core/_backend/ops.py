@@ -91,6 +91,28 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=EPI_NONE, bias=None, aux=None
     return out
 
 
+def gemm_rowsum(a, b, *, a_mn=False, b_mn=False, alpha=1.0, split_k=0, out=None, rowsum=None):
+    """fp32 C = alpha * op(A) @ op(B) and, from the same kernel, rowsum[m] += alpha * sum_k op(A)[m, k]
+    (with a = dY stored [tokens, features] and a_mn=True: weight gradient + bias gradient of a Linear).
+    `out` / `rowsum` are accumulated into when given with split_k=-2 (caller-zeroed); otherwise fresh
+    zeroed buffers are returned."""
+    _l.ensure_device()
+    _check_cuda(a, b, out, rowsum)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    K, M = a.shape if a_mn else a.shape[::-1]
+    N = b.shape[1] if b_mn else b.shape[0]
+    if out is None:
+        out = torch.zeros((M, N), device=a.device, dtype=torch.float32)
+    if rowsum is None:
+        rowsum = torch.zeros((M,), device=a.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and rowsum.dtype == torch.float32 and rowsum.is_contiguous()
+    e0 = _prof_begin()
+    _l.call("vitssl_gemm_bf16_rowsum", _p(a), _p(b), _p(out), _p(rowsum), M, N, K, a.stride(0), b.stride(0),
+            out.stride(0), int(a_mn), int(b_mn), float(alpha), int(split_k), _l.stream_ptr())
+    _prof_end(f"gemm|{M}x{N}x{K}|a_mn={int(a_mn)} b_mn={int(b_mn)} epi=0", e0, 2.0 * M * N * K)
+    return out, rowsum
+
+
 def add_layernorm_fwd(x, branch, gamma, beta, *, eps=1e-5, dropout_p=0.0, seed=0, offset=0):
     """x: fp32 [..., D] rows (last dim contiguous, uniform row pitch); branch: bf16 dense or None.
 
