@@ -103,28 +103,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp == 5) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // the whole warp walks the items and the barrier waits (uniform control flow); one elected lane
+    // issues, with descriptor low words kept in uniform registers (see gemm_sm100.cu)
+    {
       const uint32_t idesc_s = umma_idesc_bf16(128, p.kv_rows, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), av = smem_u32(sV);
+      constexpr uint32_t HI = 0x40004040u;  // SBO 1024 | descriptor version 1 | SWIZZLE_128B
+      const uint32_t q_lo = (smem_u32(sQ) >> 4) | ((16u >> 4) << 16), k_lo = (smem_u32(sK) >> 4) | ((16u >> 4) << 16);
+      const uint32_t v_lo = (smem_u32(sV) >> 4) | ((8192u >> 4) << 16);  // MN-major B operand
       const int ksteps = p.kv_rows / 16;
       int it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         mbar_wait(bar_qk, it & 1);
         if (it > 0) mbar_wait(bar_oread, (it - 1) & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem, umma_desc_sw128(aq + k * 32, 16, 1024),
-                       umma_desc_sw128(ak + k * 32, 16, 1024), idesc_s, k > 0);
-        umma_commit(bar_s);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss_lo<false>(tmem, q_lo + 2 * k, k_lo + 2 * k, HI, idesc_s, k > 0);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
         mbar_wait(bar_p, it & 1);
         mbar_wait(bar_v, it & 1);
         tc_fence_after();
-        for (int ks = 0; ks < ksteps; ++ks)  // P[128, 16 keys] = 8 packed columns per step
-          umma_bf16_ts(tmem + FWD_COL_O, tmem + ks * 8, umma_desc_sw128(av + ks * 2048, 8192, 1024),
-                       idesc_o, ks > 0);
-        umma_commit(bar_o);
+        if (elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks)  // P[128, 16 keys] = 8 packed columns per step
+            umma_bf16_ts_lo(tmem + FWD_COL_O, tmem + ks * 8, v_lo + ks * 128, HI, idesc_o, ks > 0);
+          umma_commit(bar_o);
+        }
+        __syncwarp();
       }
     }
   } else {
