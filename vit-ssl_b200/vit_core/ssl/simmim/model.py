@@ -10,7 +10,7 @@ from torch import nn
 from .._backend_access import Fb, ops
 from ...encoder_block import EncoderBlock
 from .masking import draw_mask
-from ..._backend import eager
+from ..._backend import dp, eager
 
 
 class SimMIMViT(nn.Module):
@@ -46,6 +46,7 @@ class SimMIMViT(nn.Module):
 
     @eager
     def forward(self, x, return_bool_mask=False):
+        dp.maybe_attach(self)  # data parallel under torchrun without touching the trainer
         masked, targets, bool_mask = self._encode_masked(x)
         pred = Fb.autocast_out(Fb.mlp(masked, [self.simmim_head], [False]))
         if return_bool_mask:
@@ -56,6 +57,7 @@ class SimMIMViT(nn.Module):
     def reconstruction_loss(self, x):
         """Fused objective: mean |pred - target| over the masked patches (what the reference trainer
         computes with nn.L1Loss on forward()'s outputs, simmim_trainer.py:66-67)."""
+        dp.maybe_attach(self)  # data parallel under torchrun without touching the trainer
         masked, targets, _ = self._encode_masked(x)
         pred = Fb.mlp(masked, [self.simmim_head], [False])
         return Fb.l1_loss(pred, targets)

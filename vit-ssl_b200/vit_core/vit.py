@@ -7,7 +7,7 @@ from ._backend import functional as Fb
 from .encoder_block import EncoderBlock
 from .mlp_head import MLPHead
 from .patch_embedding import ConvolutionalPatchEmbedding
-from ._backend import eager
+from ._backend import dp, eager
 
 
 class ViT(nn.Module):
@@ -22,6 +22,7 @@ class ViT(nn.Module):
 
     @eager
     def forward(self, x, return_attn=False):
+        dp.maybe_attach(self)  # data parallel under torchrun without touching the trainer
         x = self.patch_embedding(x)
         x, attn_probs = Fb.encoder_stack(self.encoder_blocks, x, return_attn)
         logits = self.classification_head(x[:, 0])
