@@ -117,3 +117,19 @@ def test_oracle_is_not_imported_by_the_product():
             if f.endswith(".py"):
                 src = open(os.path.join(dp_, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{f} references the oracle"
+
+
+def test_committed_launch_list_reproduces_the_traffic_table(tmp_path):
+    """profiles/traffic.json (read by bench.py for `roofline.traffic`) must be what
+    scripts/summarize_launches.py derives from the committed ncu launch list."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "traffic.json"
+    subprocess.run([sys.executable, os.path.join(root, "scripts", "summarize_launches.py"),
+                    os.path.join(root, "profiles", "r1_launches.csv"), str(out)], check=True, capture_output=True)
+    got, want = json.load(open(out)), json.load(open(os.path.join(root, "profiles", "traffic.json")))
+    for fam in ("gemm_tcgen05_kernel", "ln_kernel", "attn_bwd_kernel", "attn_fwd_kernel"):
+        assert got[fam] == want[fam], fam
+        assert want[fam]["launches"] > 0 and want[fam]["dram_bytes_per_launch"] > 1e6
