@@ -15,7 +15,10 @@
 namespace vitssl {
 namespace {
 
-constexpr int LN_WARPS = 4;
+#ifndef VITSSL_LN_WARPS
+#define VITSSL_LN_WARPS 4  // rows (= warps) per CTA; 2 and 8 measured slower or equal (profiles/README.md)
+#endif
+constexpr int LN_WARPS = VITSSL_LN_WARPS;
 
 struct LnFwdArgs {
   const float* x; long long ldx;          // input stream rows (pitch in elements)
