@@ -285,6 +285,26 @@ def test_dino_loss_kernel_matches_reference_and_closed_form():
     assert rel_l2(s.grad / 65536.0, sb.grad) <= 1e-2
 
 
+@pytest.mark.parametrize("G,V,B,K", [(2, 8, 6, 16384), (2, 6, 3, 65536), (1, 2, 160, 8192), (2, 3, 5, 4104)])
+def test_dino_loss_long_rows_match_the_oracle(G, V, B, K):
+    """DINO loss / gradient at head widths up to the BASELINE K = 65536 (online max/sum rescaling over
+    thousands of 8-logit groups per thread, ragged K, one global view) against the oracle on the
+    same bf16 logits."""
+    from vit_core.ssl.dino.loss import DINOLoss
+    gen = torch.Generator().manual_seed(G * 100 + V * 10 + B)
+    t = (torch.randn(G, B, K, generator=gen) * 2.0).bfloat16()
+    s0 = (torch.randn(V, B, K, generator=gen) * 1.5).bfloat16()
+    c = torch.randn(1, K, generator=gen) * 0.1
+    s = s0.cuda().requires_grad_(True)
+    loss = DINOLoss(0.05, 0.1)(t.cuda(), s, c.cuda())
+    sb = s0.double().requires_grad_(True)
+    ref = vit_ref.dino_loss(t.double(), sb, c.double(), 0.05, 0.1)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-4 * abs(ref.item()), (loss.item(), ref.item())
+    loss.backward()
+    assert rel_l2(s.grad, sb.grad) <= 1e-2
+
+
 def test_no_cpu_fallback():
     from vit_core import ViT
     from vit_core._backend.lib import VitsslError
