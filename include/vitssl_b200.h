@@ -40,6 +40,16 @@ int vitssl_num_sms(void);
  * (bench.py reports it as gpu_launches) */
 int64_t vitssl_launch_count(int reset);
 
+/* Per-launch device timing of the C-sequenced encoder stack (bench.py's roofline numbers): while a
+ * profile is open every kernel family the stack launches is bracketed by CUDA events on its stream.
+ * vitssl_profile_end() closes it and returns the number of records; vitssl_profile_read() is the ONE
+ * entry point that waits for the device (cudaEventSynchronize on the record). `kind` is
+ * "gemm|MxNxK|a_mn=. b_mn=. epi=." | "attn_fwd" | "attn_bwd" | "add_layernorm"; `work` is the
+ * algorithmic FLOPs (tensor-bound families) or bytes (add_layernorm). */
+int vitssl_profile_begin(void);
+int64_t vitssl_profile_end(void);
+int vitssl_profile_read(int64_t index, char* kind_out, int64_t kind_cap, double* work, float* ms);
+
 /* ---- GEMM: every nn.Linear / Conv2d-patchify on the path -------------------------------
  * C[M,N] = alpha * op(A) * op(B), bf16 inputs, fp32 accumulation (tcgen05.mma, TMEM).
  *   a_mn = 0: A stored [M][K] (pitch lda)      a_mn = 1: A stored [K][M]
@@ -180,6 +190,11 @@ int vitssl_multi_cast_bf16(const void* const* host_src, void* const* host_dst,
 /* teacher <- m * teacher + (1 - m) * student over parameter lists (ssl/dino/model.py:126-139). */
 int vitssl_multi_ema(void* const* host_teacher, const void* const* host_student,
                      const int64_t* host_numel, int count, float momentum, vitssl_stream_t stream);
+/* same update with the teacher's bf16 GEMM-operand shadows written in the same pass
+ * (host_shadow[i] NULL = parameter without a shadow), so the next teacher forward needs no cast. */
+int vitssl_multi_ema_shadow(void* const* host_teacher, const void* const* host_student,
+                            void* const* host_shadow, const int64_t* host_numel, int count,
+                            float momentum, vitssl_stream_t stream);
 /* out[c] = sum_r x[r,c] (bf16 in, fp32 out; out is zeroed on `stream`): bias gradients. */
 int vitssl_colsum_bf16(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out,
                        vitssl_stream_t stream);
@@ -195,6 +210,21 @@ int vitssl_im2col_bf16(const float* img, void* out, int64_t B, int64_t C, int64_
 /* raw fp32 patches of the listed flat patch ids (b*N + n): SimMIM targets (masking.py:35). */
 int vitssl_gather_patches_f32(const float* img, const int32_t* rows_idx, float* out, int64_t n_rows,
                               int64_t C, int64_t H, int64_t W, int64_t p, vitssl_stream_t stream);
+/* Input side (data/datasets.py:102-123 feed `ToTensor` output): the same two kernels
+ * reading raw uint8 [B,C,H,W] image bytes, value = byte / 255 exactly as torchvision's ToTensor
+ * computes it, so the host sends 1 byte per pixel instead of 4 and no fp32 image is ever stored. */
+int vitssl_im2col_u8_bf16(const uint8_t* img, void* out, int64_t B, int64_t C, int64_t H, int64_t W,
+                          int64_t p, vitssl_stream_t stream);
+int vitssl_gather_patches_u8_f32(const uint8_t* img, const int32_t* rows_idx, float* out, int64_t n_rows,
+                                 int64_t C, int64_t H, int64_t W, int64_t p, vitssl_stream_t stream);
+/* Bicubic resize of the positional-embedding grid (patch_embedding.py:26-48) as a sparse row
+ * interpolation: dst[i,:] = sum_t w[i,t] * src[idx[i,t],:], idx/w = [n_out, taps] tables (16 taps for
+ * bicubic; built once per grid pair on the host with torch's upsample_bicubic2d index arithmetic).
+ * Backward: dsrc (fp32 [n_in, D], zeroed on `stream`) += w[i,t] * ddst[i,:]. */
+int vitssl_interp_rows_fwd(const float* src, const int32_t* idx, const float* w, float* dst,
+                           int64_t n_out, int64_t D, int64_t taps, vitssl_stream_t stream);
+int vitssl_interp_rows_bwd(const float* ddst, const int32_t* idx, const float* w, float* dsrc,
+                           int64_t n_in, int64_t n_out, int64_t D, int64_t taps, vitssl_stream_t stream);
 /* x[b,s,:] = (CLS | mask_token | proj[b,n,:]) + pos[s,:]   (patch_embedding.py:61-63,94-95;
  * ssl/simmim/model.py:47-49). cls NULL -> no CLS row (S = N); mask (uint8 [B*N]) NULL -> none. */
 int vitssl_embed_tokens_fwd(const void* proj, const float* cls, const float* pos,
@@ -236,6 +266,24 @@ int64_t vitssl_randperm_offset_per_call(int64_t n);
 int vitssl_l1_loss_fwd(const void* pred, const float* target, void* sign, float* loss, int64_t n,
                        vitssl_stream_t stream);
 
+/* d(pred) = sign * grad_out / n (bf16); grad_out is a DEVICE scalar (GradScaler-scaled upstream
+ * gradient), so backward needs no host read and no re-read of pred/target. */
+int vitssl_l1_loss_bwd(const void* sign, const float* grad_out, void* dpred, int64_t n,
+                       vitssl_stream_t stream);
+
+/* ---- optimizer step ------------------------------------------------------------
+ * Fused multi-tensor AdamW replacing `scaler.step(optimizer)` on torch.optim.AdamW
+ * (utils/train_utils.py:25-29, utils/trainers/simmim_trainer.py:69-71, base_trainer.py:44): one pass
+ * over fp32 (param, grad, exp_avg, exp_avg_sq) with the GradScaler unscale (grad / *grad_scale) and
+ * skip (*found_inf != 0) folded in, torch's fused-AdamW arithmetic, and the bf16 GEMM-operand shadow
+ * written in the same pass (host_shadow[i] may be NULL). host_* are HOST arrays of `count` DEVICE
+ * pointers; host_step[i] is the tensor's fp32 device step counter (advanced here unless found_inf). */
+int vitssl_adamw_step(void* const* host_param, const void* const* host_grad, void* const* host_exp_avg,
+                      void* const* host_exp_avg_sq, void* const* host_shadow, void* const* host_step,
+                      const int64_t* host_numel, int count, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, const float* grad_scale, const float* found_inf,
+                      vitssl_stream_t stream);
+
 /* ---- DINO objective ------------------------------------------------------------------------ */
 /* F.normalize(dim=1) (ssl/dino/head.py:21), bf16 rows. */
 int vitssl_l2norm_fwd(const void* x, void* y, float* inv_norm, int64_t rows, int64_t D,
@@ -253,7 +301,7 @@ int vitssl_center_ema(const float* center, const float* colsum, float* out, int6
                       float inv_rows, vitssl_stream_t stream);
 /* DINOLoss (ssl/dino/loss.py:13-29) for teacher bf16 [G,B,K], student bf16 [V,B,K], center [K]:
  * loss[0] = -(1/(G B K)) sum_b sum_k (sum_g softmax((T_g-c)/tt))(sum_v log_softmax(S_v/ts)).
- * t_stats [G,B,2] and s_lse [V,B] are saved for backward. G <= 2, V <= 12, K % 8 == 0. */
+ * t_stats [G,B,2] and s_lse [V,B] are saved for backward. G <= 4, V <= 12 (callers chunk more views: the loss is additive over view groups), K % 8 == 0. */
 int vitssl_dino_loss_fwd(const void* teacher, const void* student, const float* center, float* loss,
                          float* t_stats, float* s_lse, int64_t G, int64_t V, int64_t B, int64_t K,
                          float teacher_temp, float student_temp, vitssl_stream_t stream);

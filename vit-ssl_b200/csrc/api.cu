@@ -4,6 +4,8 @@
 #include <cudaTypedefs.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <stdarg.h>
 #include <string.h>
 
@@ -33,6 +35,30 @@ int check_launch(const char* what) {
     return VITSSL_ERR_CUDA;
   }
   return VITSSL_OK;
+}
+
+// ---- per-launch profile (bench.py's roofline numbers for the C-sequenced encoder stack) ----------
+struct ProfRec { char kind[40]; double work; cudaEvent_t e0, e1; };
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;  // forward runs on the main thread, backward on autograd's worker
+static std::vector<ProfRec> g_prof;
+
+bool prof_on() { return g_prof_on.load(std::memory_order_relaxed); }
+
+void ProfScope::begin(const char* kind, double work) {
+  ProfRec r{};
+  strncpy(r.kind, kind, sizeof(r.kind) - 1);
+  r.work = work;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, stream_);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  idx_ = static_cast<int>(g_prof.size()) - 1;
+}
+
+void ProfScope::end() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx_ < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[idx_].e1, stream_);
 }
 
 bool pdl_enabled() {
@@ -137,6 +163,34 @@ extern "C" int64_t vitssl_launch_count(int reset) {
   const long long v = vitssl::g_launches.load();
   if (reset) vitssl::g_launches.store(0);
   return v;
+}
+
+extern "C" int vitssl_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(vitssl::g_prof_mu);
+  for (auto& r : vitssl::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  vitssl::g_prof.clear();
+  vitssl::g_prof_on.store(true);
+  return 0;
+}
+
+extern "C" int64_t vitssl_profile_end(void) {
+  vitssl::g_prof_on.store(false);
+  std::lock_guard<std::mutex> lk(vitssl::g_prof_mu);
+  return static_cast<int64_t>(vitssl::g_prof.size());
+}
+
+extern "C" int vitssl_profile_read(int64_t index, char* kind_out, int64_t kind_cap, double* work, float* ms) {
+  std::lock_guard<std::mutex> lk(vitssl::g_prof_mu);
+  VITSSL_REQUIRE(index >= 0 && index < static_cast<int64_t>(vitssl::g_prof.size()) && kind_out && kind_cap > 0 && work && ms,
+                 VITSSL_ERR_ARG, "profile_read: bad index or null output");
+  const auto& r = vitssl::g_prof[index];
+  cudaError_t err = cudaEventSynchronize(r.e1);  // the one place this library waits for the device
+  if (err == cudaSuccess) err = cudaEventElapsedTime(ms, r.e0, r.e1);
+  VITSSL_REQUIRE(err == cudaSuccess, VITSSL_ERR_CUDA, "profile_read: %s", cudaGetErrorString(err));
+  strncpy(kind_out, r.kind, kind_cap - 1);
+  kind_out[kind_cap - 1] = 0;
+  *work = r.work;
+  return 0;
 }
 
 extern "C" int vitssl_device_check(void) {

@@ -34,6 +34,24 @@ enum : int {
 };
 
 int num_sms();  // cached SM count of the current device
+
+// Per-launch device timing of the C-sequenced paths (vitssl_profile_begin / _end, api.cu). While a
+// profile is open, a ProfScope records a CUDA event on `stream` before and after the launches it
+// brackets, tagged with a kernel family and its algorithmic work (FLOPs or bytes). Closed: no-op.
+bool prof_on();
+struct ProfScope {
+  ProfScope(const char* kind, double work, cudaStream_t stream) : idx_(-1), stream_(stream) {
+    if (prof_on()) begin(kind, work);
+  }
+  ~ProfScope() { if (idx_ >= 0) end(); }
+  ProfScope(const ProfScope&) = delete;
+  ProfScope& operator=(const ProfScope&) = delete;
+ private:
+  void begin(const char* kind, double work);
+  void end();
+  int idx_;
+  cudaStream_t stream_;
+};
 bool pdl_enabled();  // programmatic dependent launch for the hot kernels (VITSSL_PDL=0 disables)
 
 // Launch with programmatic stream serialization: the grid may begin (prologue: barrier init,

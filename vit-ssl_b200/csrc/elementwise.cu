@@ -189,8 +189,11 @@ __global__ void colsum_generic_kernel(const __nv_bfloat16* __restrict__ x, long 
 // im2col + cast: img fp32 [B,C,H,W] -> patches bf16 [B*gh*gw, C*p*p], feature order (c,ph,pw)
 // (nn.Unfold, ssl/simmim/model.py:43; equals the Conv2d(k=s=p) im2col, patch_embedding.py:22,79)
 // ---------------------------------------------------------------------------------------
-template <int VEC>
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ img,
+// uint8 sources are raw image bytes; value = byte / 255 (torchvision ToTensor), §8(f)3
+__device__ __forceinline__ float u8_to_unit(uint32_t b) { return __fdiv_rn(static_cast<float>(b), 255.0f); }
+
+template <int VEC, typename SRC>
+__global__ void __launch_bounds__(256) im2col_kernel(const SRC* __restrict__ img,
                                                      __nv_bfloat16* __restrict__ out, int B, int C, int H,
                                                      int W, int p, long long total_groups) {
   const long long g = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
@@ -201,22 +204,34 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
   const long long patch = e / P;
   const int gx = (int)(patch % gw), gy = (int)((patch / gw) % gh), b = (int)(patch / (static_cast<long long>(gw) * gh));
   const int c = f / (p * p), ph = (f / p) % p, pw = f % p;
-  const float* src = img + ((static_cast<long long>(b) * C + c) * H + gy * p + ph) * W + gx * p + pw;
+  const SRC* src = img + ((static_cast<long long>(b) * C + c) * H + gy * p + ph) * W + gx * p + pw;
   if constexpr (VEC == 8) {
-    const float4 v0 = *reinterpret_cast<const float4*>(src);
-    const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+    float v[8];
+    if constexpr (sizeof(SRC) == 1) {
+      const uint2 q = *reinterpret_cast<const uint2*>(src);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = u8_to_unit((q.x >> (8 * i)) & 0xffu);
+        v[4 + i] = u8_to_unit((q.y >> (8 * i)) & 0xffu);
+      }
+    } else {
+      const float4 v0 = *reinterpret_cast<const float4*>(src);
+      const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+      v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+    }
     uint4 o;
-    o.x = pack_bf16(v0.x, v0.y); o.y = pack_bf16(v0.z, v0.w);
-    o.z = pack_bf16(v1.x, v1.y); o.w = pack_bf16(v1.z, v1.w);
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
     *reinterpret_cast<uint4*>(out + e) = o;
   } else {
-    out[e] = __float2bfloat16_rn(*src);
+    if constexpr (sizeof(SRC) == 1) out[e] = __float2bfloat16_rn(u8_to_unit(*src));
+    else out[e] = __float2bfloat16_rn(*src);
   }
 }
 
 // gather of raw fp32 patches for the rows listed in idx (SimMIM targets, masking.py:35)
-template <int VEC>
-__global__ void __launch_bounds__(256) gather_patches_kernel(const float* __restrict__ img,
+template <int VEC, typename SRC>
+__global__ void __launch_bounds__(256) gather_patches_kernel(const SRC* __restrict__ img,
                                                              const int* __restrict__ idx,
                                                              float* __restrict__ out, int C, int H, int W,
                                                              int p, long long total_groups) {
@@ -228,11 +243,44 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(const float* __rest
   const long long patch = idx[e / P];
   const int gx = (int)(patch % gw), gy = (int)((patch / gw) % gh), b = (int)(patch / (static_cast<long long>(gw) * gh));
   const int c = f / (p * p), ph = (f / p) % p, pw = f % p;
-  const float* src = img + ((static_cast<long long>(b) * C + c) * H + gy * p + ph) * W + gx * p + pw;
+  const SRC* src = img + ((static_cast<long long>(b) * C + c) * H + gy * p + ph) * W + gx * p + pw;
   if constexpr (VEC == 4) {
-    *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<const float4*>(src);
+    if constexpr (sizeof(SRC) == 1) {
+      const uint32_t q = *reinterpret_cast<const uint32_t*>(src);
+      *reinterpret_cast<float4*>(out + e) = make_float4(u8_to_unit(q & 0xffu), u8_to_unit((q >> 8) & 0xffu),
+                                                        u8_to_unit((q >> 16) & 0xffu), u8_to_unit(q >> 24));
+    } else {
+      *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<const float4*>(src);
+    }
   } else {
-    out[e] = *src;
+    if constexpr (sizeof(SRC) == 1) out[e] = u8_to_unit(*src);
+    else out[e] = *src;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// sparse row interpolation: dst[i,:] = sum_t w[i,t] * src[idx[i,t],:]  (bicubic resize of the
+// positional-embedding grid, patch_embedding.py:26-48, as a 16-tap table built once on the host).
+// Backward scatters: dsrc[idx[i,t],:] += w[i,t] * ddst[i,:]  (dsrc zeroed by the entry point).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) interp_rows_fwd_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                              const float* __restrict__ w, float* __restrict__ dst,
+                                                              int n_out, int D, int taps) {
+  const int i = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += 128) {
+    float acc = 0.f;
+    for (int t = 0; t < taps; ++t) acc = fmaf(w[i * taps + t], src[static_cast<long long>(idx[i * taps + t]) * D + d], acc);
+    dst[static_cast<long long>(i) * D + d] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(128) interp_rows_bwd_kernel(const float* __restrict__ ddst, const int* __restrict__ idx,
+                                                              const float* __restrict__ w, float* __restrict__ dsrc,
+                                                              int n_out, int D, int taps) {
+  const int i = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += 128) {
+    const float gval = ddst[static_cast<long long>(i) * D + d];
+    for (int t = 0; t < taps; ++t) atomicAdd(dsrc + static_cast<long long>(idx[i * taps + t]) * D + d, w[i * taps + t] * gval);
   }
 }
 
@@ -491,35 +539,77 @@ extern "C" int vitssl_colsum_bf16_acc(const void* x, int64_t ld, int64_t rows, i
   return check_launch("colsum_bf16");
 }
 
-extern "C" int vitssl_im2col_bf16(const float* img, void* out, int64_t B, int64_t C, int64_t H,
-                                  int64_t W, int64_t p, cudaStream_t stream) {
+namespace {
+template <typename SRC>
+int im2col_launch(const SRC* img, void* out, int64_t B, int64_t C, int64_t H, int64_t W, int64_t p, cudaStream_t stream) {
   VITSSL_REQUIRE(img && out && B > 0 && C > 0 && p > 0, VITSSL_ERR_ARG, "im2col_bf16: bad args");
   VITSSL_REQUIRE(H % p == 0 && W % p == 0, VITSSL_ERR_SHAPE,
                  "im2col_bf16: image %lldx%lld not divisible by patch %lld", (long long)H, (long long)W, (long long)p);
   const long long total = B * C * H * W;
-  if (p % 8 == 0 && W % 4 == 0 && aligned16(img) && aligned16(out)) {
+  const bool src_ok = sizeof(SRC) == 1 ? (W % 8 == 0 && (reinterpret_cast<uintptr_t>(img) & 7) == 0) : (W % 4 == 0 && aligned16(img));
+  if (p % 8 == 0 && src_ok && aligned16(out)) {
     const long long groups = total / 8;
-    im2col_kernel<8><<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(img, (__nv_bfloat16*)out, (int)B, (int)C, (int)H, (int)W, (int)p, groups);
+    im2col_kernel<8, SRC><<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(img, (__nv_bfloat16*)out, (int)B, (int)C, (int)H, (int)W, (int)p, groups);
   } else {
-    im2col_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(img, (__nv_bfloat16*)out, (int)B, (int)C, (int)H, (int)W, (int)p, total);
+    im2col_kernel<1, SRC><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(img, (__nv_bfloat16*)out, (int)B, (int)C, (int)H, (int)W, (int)p, total);
   }
   return check_launch("im2col_bf16");
+}
+
+template <typename SRC>
+int gather_patches_launch(const SRC* img, const int32_t* rows_idx, float* out, int64_t n_rows, int64_t C, int64_t H,
+                          int64_t W, int64_t p, cudaStream_t stream) {
+  VITSSL_REQUIRE(img && rows_idx && out && n_rows >= 0, VITSSL_ERR_ARG, "gather_patches_f32: bad args");
+  VITSSL_REQUIRE(H % p == 0 && W % p == 0, VITSSL_ERR_SHAPE, "gather_patches_f32: image not divisible by patch");
+  if (n_rows == 0) return 0;
+  const long long total = n_rows * C * p * p;
+  const bool src_ok = sizeof(SRC) == 1 ? (reinterpret_cast<uintptr_t>(img) & 3) == 0 : aligned16(img);
+  if (p % 4 == 0 && W % 4 == 0 && src_ok && aligned16(out)) {
+    const long long groups = total / 4;
+    gather_patches_kernel<4, SRC><<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(img, rows_idx, out, (int)C, (int)H, (int)W, (int)p, groups);
+  } else {
+    gather_patches_kernel<1, SRC><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(img, rows_idx, out, (int)C, (int)H, (int)W, (int)p, total);
+  }
+  return check_launch("gather_patches_f32");
+}
+}  // namespace
+
+extern "C" int vitssl_im2col_bf16(const float* img, void* out, int64_t B, int64_t C, int64_t H,
+                                  int64_t W, int64_t p, cudaStream_t stream) {
+  return im2col_launch(img, out, B, C, H, W, p, stream);
+}
+
+extern "C" int vitssl_im2col_u8_bf16(const uint8_t* img, void* out, int64_t B, int64_t C, int64_t H,
+                                     int64_t W, int64_t p, cudaStream_t stream) {
+  return im2col_launch(img, out, B, C, H, W, p, stream);
 }
 
 extern "C" int vitssl_gather_patches_f32(const float* img, const int32_t* rows_idx, float* out,
                                          int64_t n_rows, int64_t C, int64_t H, int64_t W, int64_t p,
                                          cudaStream_t stream) {
-  VITSSL_REQUIRE(img && rows_idx && out && n_rows >= 0, VITSSL_ERR_ARG, "gather_patches_f32: bad args");
-  VITSSL_REQUIRE(H % p == 0 && W % p == 0, VITSSL_ERR_SHAPE, "gather_patches_f32: image not divisible by patch");
-  if (n_rows == 0) return 0;
-  const long long total = n_rows * C * p * p;
-  if (p % 4 == 0 && W % 4 == 0 && aligned16(img) && aligned16(out)) {
-    const long long groups = total / 4;
-    gather_patches_kernel<4><<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(img, rows_idx, out, (int)C, (int)H, (int)W, (int)p, groups);
-  } else {
-    gather_patches_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(img, rows_idx, out, (int)C, (int)H, (int)W, (int)p, total);
-  }
-  return check_launch("gather_patches_f32");
+  return gather_patches_launch(img, rows_idx, out, n_rows, C, H, W, p, stream);
+}
+
+extern "C" int vitssl_gather_patches_u8_f32(const uint8_t* img, const int32_t* rows_idx, float* out,
+                                            int64_t n_rows, int64_t C, int64_t H, int64_t W, int64_t p,
+                                            cudaStream_t stream) {
+  return gather_patches_launch(img, rows_idx, out, n_rows, C, H, W, p, stream);
+}
+
+extern "C" int vitssl_interp_rows_fwd(const float* src, const int32_t* idx, const float* w, float* dst,
+                                      int64_t n_out, int64_t D, int64_t taps, cudaStream_t stream) {
+  VITSSL_REQUIRE(src && idx && w && dst && n_out > 0 && D > 0 && taps > 0, VITSSL_ERR_ARG, "interp_rows_fwd: bad args");
+  interp_rows_fwd_kernel<<<(unsigned)n_out, 128, 0, stream>>>(src, idx, w, dst, (int)n_out, (int)D, (int)taps);
+  return check_launch("interp_rows_fwd");
+}
+
+extern "C" int vitssl_interp_rows_bwd(const float* ddst, const int32_t* idx, const float* w, float* dsrc,
+                                      int64_t n_in, int64_t n_out, int64_t D, int64_t taps, cudaStream_t stream) {
+  VITSSL_REQUIRE(ddst && idx && w && dsrc && n_in > 0 && n_out > 0 && D > 0 && taps > 0, VITSSL_ERR_ARG,
+                 "interp_rows_bwd: bad args");
+  cudaMemsetAsync(dsrc, 0, sizeof(float) * n_in * D, stream);
+  interp_rows_bwd_kernel<<<(unsigned)n_out, 128, 0, stream>>>(ddst, idx, w, dsrc, (int)n_out, (int)D, (int)taps);
+  return check_launch("interp_rows_bwd");
 }
 
 extern "C" int vitssl_embed_tokens_fwd(const void* proj, const float* cls, const float* pos,

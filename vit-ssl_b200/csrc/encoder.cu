@@ -20,6 +20,26 @@ using namespace vitssl;
     if (rc_ != 0) return rc_;     \
   } while (0)
 
+// Per-launch timing while a profile is open (vitssl_profile_begin): CUDA events on `stream` around
+// the launch, tagged with the kernel family and its algorithmic work, so that bench.py's roofline
+// numbers are taken on THIS sequencing path — the one the timed step runs.
+namespace {
+struct Kind { char s[40]; };
+inline Kind gemm_kind(int64_t M, int64_t N, int64_t K, int a_mn, int b_mn, int epi) {
+  Kind k;
+  snprintf(k.s, sizeof(k.s), "gemm|%lldx%lldx%lld|a_mn=%d b_mn=%d epi=%d", (long long)M, (long long)N, (long long)K,
+           a_mn, b_mn, epi);
+  return k;
+}
+inline double gemm_flops(int64_t M, int64_t N, int64_t K) { return 2.0 * (double)M * (double)N * (double)K; }
+inline double attn_flops(int64_t B, int64_t H, int64_t S) { return 4.0 * (double)B * (double)H * (double)S * (double)S * 64.0; }
+}  // namespace
+#define VITSSL_TIMED(kind, work, call)        \
+  do {                                        \
+    ProfScope ps_((kind), (work), stream);    \
+    VITSSL_TRY(call);                         \
+  } while (0)
+
 extern "C" int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* a, cudaStream_t stream) {
   VITSSL_REQUIRE(a != nullptr && a->L >= 1, VITSSL_ERR_ARG, "encoder_stack_fwd: bad args");
   const int64_t B = a->B, S = a->S, D = a->D, H = a->H, F = a->F, L = a->L;
@@ -34,33 +54,42 @@ extern "C" int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* a, cudaSt
   for (int64_t l = 0; l < L; ++l) {
     // x = x + drop(branch); xn1 = LN1(x)                                   encoder_block.py:40-41
     float* xs = (l == 0) ? nullptr : a->xs[l];
-    VITSSL_TRY(vitssl_add_layernorm_fwd(stream_in, D, branch, xs, a->g1[l], a->be1[l], a->xn1[l], a->mean1[l],
-                                        a->rstd1[l], M, D, a->eps, branch ? p : 0.f, a->seed,
-                                        (uint64_t)(l > 0 ? 3 * l - 1 : 0), stream));
+    VITSSL_TIMED("add_layernorm", (double)M * D * (branch ? 12 : 6),
+                 vitssl_add_layernorm_fwd(stream_in, D, branch, xs, a->g1[l], a->be1[l], a->xn1[l], a->mean1[l],
+                                          a->rstd1[l], M, D, a->eps, branch ? p : 0.f, a->seed,
+                                          (uint64_t)(l > 0 ? 3 * l - 1 : 0), stream));
     const float* x_l = (l == 0) ? a->x_in : xs;
     // fused QKV projection                                                   attention.py:82-84
-    VITSSL_TRY(vitssl_gemm_bf16(a->xn1[l], a->wqkv[l], a->qkv[l], M, 3 * D, D, D, D, 3 * D, 0, 0, VITSSL_EPI_NONE,
-                                nullptr, nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));
+    VITSSL_TIMED(gemm_kind(M, 3 * D, D, 0, 0, 0).s, gemm_flops(M, 3 * D, D),
+                 vitssl_gemm_bf16(a->xn1[l], a->wqkv[l], a->qkv[l], M, 3 * D, D, D, D, 3 * D, 0, 0, VITSSL_EPI_NONE,
+                                  nullptr, nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(a->qkv[l]);
-    VITSSL_TRY(vitssl_attention_fwd(qkv, qkv + D, qkv + 2 * D, 3 * D, 3 * D, 3 * D, a->ctx[l], D, a->lse[l], B, H, S,
-                                    S, scale, stream));                     // attention.py:20-23
-    VITSSL_TRY(vitssl_gemm_bf16(a->ctx[l], a->wo[l], a->y1, M, D, D, D, D, D, 0, 0, VITSSL_EPI_NONE, nullptr,
-                                nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));  // attention.py:105
+    VITSSL_TIMED("attn_fwd", attn_flops(B, H, S),
+                 vitssl_attention_fwd(qkv, qkv + D, qkv + 2 * D, 3 * D, 3 * D, 3 * D, a->ctx[l], D, a->lse[l], B, H, S,
+                                      S, scale, stream));                     // attention.py:20-23
+    VITSSL_TIMED(gemm_kind(M, D, D, 0, 0, 0).s, gemm_flops(M, D, D),
+                 vitssl_gemm_bf16(a->ctx[l], a->wo[l], a->y1, M, D, D, D, D, D, 0, 0, VITSSL_EPI_NONE, nullptr,
+                                  nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));  // attention.py:105
     // x = x + drop(attn); xn2 = LN2(x)                                     encoder_block.py:45-48
-    VITSSL_TRY(vitssl_add_layernorm_fwd(x_l, D, a->y1, a->xmid[l], a->g2[l], a->be2[l], a->xn2[l], a->mean2[l],
-                                        a->rstd2[l], M, D, a->eps, p, a->seed, (uint64_t)(3 * l), stream));
+    VITSSL_TIMED("add_layernorm", (double)M * D * 12,
+                 vitssl_add_layernorm_fwd(x_l, D, a->y1, a->xmid[l], a->g2[l], a->be2[l], a->xn2[l], a->mean2[l],
+                                          a->rstd2[l], M, D, a->eps, p, a->seed, (uint64_t)(3 * l), stream));
     // FFN: u = xn2 W1^T + b1 (saved), h = drop(gelu(u)); y2 = h W2^T + b2   feed_forward.py:26-28
-    VITSSL_TRY(vitssl_gemm_bf16(a->xn2[l], a->w1[l], a->h[l], M, F, D, D, D, F, 0, 0, VITSSL_EPI_BIAS_GELU, a->b1[l],
-                                a->u[l], F, 1.0f, 0, 0, p, a->seed, (uint64_t)(3 * l + 1), stream));
+    VITSSL_TIMED(gemm_kind(M, F, D, 0, 0, 2).s, gemm_flops(M, F, D),
+                 vitssl_gemm_bf16(a->xn2[l], a->w1[l], a->h[l], M, F, D, D, D, F, 0, 0, VITSSL_EPI_BIAS_GELU, a->b1[l],
+                                  a->u[l], F, 1.0f, 0, 0, p, a->seed, (uint64_t)(3 * l + 1), stream));
     void* y2 = a->y2[l & 1];
-    VITSSL_TRY(vitssl_gemm_bf16(a->h[l], a->w2[l], y2, M, D, F, F, F, D, 0, 0, VITSSL_EPI_BIAS, a->b2[l], nullptr, 0,
-                                1.0f, 0, 0, 0.f, 0, 0, stream));
+    VITSSL_TIMED(gemm_kind(M, D, F, 0, 0, 1).s, gemm_flops(M, D, F),
+                 vitssl_gemm_bf16(a->h[l], a->w2[l], y2, M, D, F, F, F, D, 0, 0, VITSSL_EPI_BIAS, a->b2[l], nullptr, 0,
+                                  1.0f, 0, 0, 0.f, 0, 0, stream));
     stream_in = a->xmid[l];
     branch = y2;
   }
   // final residual add: out = x + drop(ffn)                                 encoder_block.py:51-52
-  return vitssl_add_layernorm_fwd(stream_in, D, branch, a->out, nullptr, nullptr, nullptr, nullptr, nullptr, M, D,
-                                  a->eps, p, a->seed, (uint64_t)(3 * L - 1), stream);
+  VITSSL_TIMED("add_layernorm", (double)M * D * 10,
+               vitssl_add_layernorm_fwd(stream_in, D, branch, a->out, nullptr, nullptr, nullptr, nullptr, nullptr, M, D,
+                                        a->eps, p, a->seed, (uint64_t)(3 * L - 1), stream));
+  return 0;
 }
 
 extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaStream_t stream) {
@@ -76,8 +105,9 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
   const float* gs;  // gradient on the residual stream
   if (l_hi == L) {
     // gradient of the final add: the stream gradient passes through, the branch gets mask/(1-p) * g
-    VITSSL_TRY(vitssl_add_layernorm_bwd_acc(nullptr, nullptr, 0, nullptr, nullptr, nullptr, a->gout, D, nullptr, 0,
-                                            a->dbranch, nullptr, nullptr, M, D, p, f->seed, (uint64_t)(3 * L - 1), stream));
+    VITSSL_TIMED("add_layernorm", (double)M * D * 6,
+                 vitssl_add_layernorm_bwd_acc(nullptr, nullptr, 0, nullptr, nullptr, nullptr, a->gout, D, nullptr, 0,
+                                              a->dbranch, nullptr, nullptr, M, D, p, f->seed, (uint64_t)(3 * L - 1), stream));
     gs = a->gout;
   } else {
     gs = a->gs[1];  // left there (with dbranch) by the previous call
@@ -85,46 +115,61 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
   for (int64_t l = l_hi - 1; l >= l_lo; --l) {
     const void* dy2 = a->dbranch;
     // FFN backward
-    VITSSL_TRY(vitssl_gemm_bf16(dy2, f->w2[l], a->du, M, F, D, D, F, F, 0, 1, VITSSL_EPI_DGELU, nullptr, f->u[l], F,
-                                1.0f, 0, 0, p, f->seed, (uint64_t)(3 * l + 1), stream));
+    VITSSL_TIMED(gemm_kind(M, F, D, 0, 1, 3).s, gemm_flops(M, F, D),
+                 vitssl_gemm_bf16(dy2, f->w2[l], a->du, M, F, D, D, F, F, 0, 1, VITSSL_EPI_DGELU, nullptr, f->u[l], F,
+                                  1.0f, 0, 0, p, f->seed, (uint64_t)(3 * l + 1), stream));
     // dW2 = dy2^T h with db2 = colsum(dy2) from the same kernel (ones-operand MMA); shapes the fused
     // form does not cover (CTA pairs) fall back to GEMM + column-sum pass
-    if (vitssl_gemm_bf16_rowsum(dy2, f->h[l], a->dw2[l], a->db2[l], D, F, M, D, F, F, 1, 1, 1.0f, -2, stream) != 0) {
-      VITSSL_TRY(vitssl_gemm_bf16(dy2, f->h[l], a->dw2[l], D, F, M, D, F, F, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
-                                  1.0f, 1, -2, 0.f, 0, 0, stream));
-      VITSSL_TRY(vitssl_colsum_bf16_acc(dy2, D, M, D, a->db2[l], stream));
+    {
+      ProfScope ps_(gemm_kind(D, F, M, 1, 1, 0).s, gemm_flops(D, F, M), stream);
+      if (vitssl_gemm_bf16_rowsum(dy2, f->h[l], a->dw2[l], a->db2[l], D, F, M, D, F, F, 1, 1, 1.0f, -2, stream) != 0) {
+        VITSSL_TRY(vitssl_gemm_bf16(dy2, f->h[l], a->dw2[l], D, F, M, D, F, F, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
+                                    1.0f, 1, -2, 0.f, 0, 0, stream));
+        VITSSL_TRY(vitssl_colsum_bf16_acc(dy2, D, M, D, a->db2[l], stream));
+      }
     }
-    VITSSL_TRY(vitssl_gemm_bf16(a->du, f->w1[l], a->dxn, M, D, F, F, D, D, 0, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
-                                1.0f, 0, 0, 0.f, 0, 0, stream));
-    if (vitssl_gemm_bf16_rowsum(a->du, f->xn2[l], a->dw1[l], a->db1[l], F, D, M, F, D, D, 1, 1, 1.0f, -2, stream) != 0) {
-      VITSSL_TRY(vitssl_gemm_bf16(a->du, f->xn2[l], a->dw1[l], F, D, M, F, D, D, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr,
-                                  0, 1.0f, 1, -2, 0.f, 0, 0, stream));
-      VITSSL_TRY(vitssl_colsum_bf16_acc(a->du, F, M, F, a->db1[l], stream));
+    VITSSL_TIMED(gemm_kind(M, D, F, 0, 1, 0).s, gemm_flops(M, D, F),
+                 vitssl_gemm_bf16(a->du, f->w1[l], a->dxn, M, D, F, F, D, D, 0, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
+                                  1.0f, 0, 0, 0.f, 0, 0, stream));
+    {
+      ProfScope ps_(gemm_kind(F, D, M, 1, 1, 0).s, gemm_flops(F, D, M), stream);
+      if (vitssl_gemm_bf16_rowsum(a->du, f->xn2[l], a->dw1[l], a->db1[l], F, D, M, F, D, D, 1, 1, 1.0f, -2, stream) != 0) {
+        VITSSL_TRY(vitssl_gemm_bf16(a->du, f->xn2[l], a->dw1[l], F, D, M, F, D, D, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr,
+                                    0, 1.0f, 1, -2, 0.f, 0, 0, stream));
+        VITSSL_TRY(vitssl_colsum_bf16_acc(a->du, F, M, F, a->db1[l], stream));
+      }
     }
     // LN2 + residual: gs <- d(xmid), dy1 = dropout-masked gradient of the attention branch
     float* gs_mid = a->gs[0];
-    VITSSL_TRY(vitssl_add_layernorm_bwd_acc(a->dxn, f->xmid[l], D, f->mean2[l], f->rstd2[l], f->g2[l], gs, D, gs_mid, D,
-                                        a->dbranch, a->dg2[l], a->dbe2[l], M, D, p, f->seed, (uint64_t)(3 * l),
-                                        stream));
+    VITSSL_TIMED("add_layernorm", (double)M * D * 16,
+                 vitssl_add_layernorm_bwd_acc(a->dxn, f->xmid[l], D, f->mean2[l], f->rstd2[l], f->g2[l], gs, D, gs_mid, D,
+                                              a->dbranch, a->dg2[l], a->dbe2[l], M, D, p, f->seed, (uint64_t)(3 * l),
+                                              stream));
     const void* dy1 = a->dbranch;
-    VITSSL_TRY(vitssl_gemm_bf16(dy1, f->wo[l], a->dctx, M, D, D, D, D, D, 0, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
-                                1.0f, 0, 0, 0.f, 0, 0, stream));
-    VITSSL_TRY(vitssl_gemm_bf16(dy1, f->ctx[l], a->dwo[l], D, D, M, D, D, D, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
-                                1.0f, 1, -2, 0.f, 0, 0, stream));
+    VITSSL_TIMED(gemm_kind(M, D, D, 0, 1, 0).s, gemm_flops(M, D, D),
+                 vitssl_gemm_bf16(dy1, f->wo[l], a->dctx, M, D, D, D, D, D, 0, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
+                                  1.0f, 0, 0, 0.f, 0, 0, stream));
+    VITSSL_TIMED(gemm_kind(D, D, M, 1, 1, 0).s, gemm_flops(D, D, M),
+                 vitssl_gemm_bf16(dy1, f->ctx[l], a->dwo[l], D, D, M, D, D, D, 1, 1, VITSSL_EPI_NONE, nullptr, nullptr, 0,
+                                  1.0f, 1, -2, 0.f, 0, 0, stream));
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(f->qkv[l]);
     __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv);
-    VITSSL_TRY(vitssl_attention_bwd(qkv, qkv + D, qkv + 2 * D, 3 * D, 3 * D, 3 * D, f->ctx[l], a->dctx, D, f->lse[l],
-                                    dqkv, 3 * D, dqkv + D, 3 * D, dqkv + 2 * D, 3 * D, B, H, S, S, scale, stream));
-    VITSSL_TRY(vitssl_gemm_bf16(dqkv, f->wqkv[l], a->dxn, M, D, 3 * D, 3 * D, D, D, 0, 1, VITSSL_EPI_NONE, nullptr,
-                                nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));
-    VITSSL_TRY(vitssl_gemm_bf16(dqkv, f->xn1[l], a->dwqkv[l], 3 * D, D, M, 3 * D, D, D, 1, 1, VITSSL_EPI_NONE, nullptr,
-                                nullptr, 0, 1.0f, 1, -2, 0.f, 0, 0, stream));
+    VITSSL_TIMED("attn_bwd", 2.5 * attn_flops(B, H, S),
+                 vitssl_attention_bwd(qkv, qkv + D, qkv + 2 * D, 3 * D, 3 * D, 3 * D, f->ctx[l], a->dctx, D, f->lse[l],
+                                      dqkv, 3 * D, dqkv + D, 3 * D, dqkv + 2 * D, 3 * D, B, H, S, S, scale, stream));
+    VITSSL_TIMED(gemm_kind(M, D, 3 * D, 0, 1, 0).s, gemm_flops(M, D, 3 * D),
+                 vitssl_gemm_bf16(dqkv, f->wqkv[l], a->dxn, M, D, 3 * D, 3 * D, D, D, 0, 1, VITSSL_EPI_NONE, nullptr,
+                                  nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));
+    VITSSL_TIMED(gemm_kind(3 * D, D, M, 1, 1, 0).s, gemm_flops(3 * D, D, M),
+                 vitssl_gemm_bf16(dqkv, f->xn1[l], a->dwqkv[l], 3 * D, D, M, 3 * D, D, D, 1, 1, VITSSL_EPI_NONE, nullptr,
+                                  nullptr, 0, 1.0f, 1, -2, 0.f, 0, 0, stream));
     // LN1 + residual: gs <- d(block input); for l > 0 also the masked gradient of block l-1's FFN
     const float* x_l = (l == 0) ? f->x_in : f->xs[l];
     float* gs_in = (l == 0) ? a->dx : a->gs[1];
-    VITSSL_TRY(vitssl_add_layernorm_bwd_acc(a->dxn, x_l, D, f->mean1[l], f->rstd1[l], f->g1[l], gs_mid, D, gs_in, D,
-                                        l > 0 ? a->dbranch : nullptr, a->dg1[l], a->dbe1[l], M, D, l > 0 ? p : 0.f,
-                                        f->seed, (uint64_t)(l > 0 ? 3 * l - 1 : 0), stream));
+    VITSSL_TIMED("add_layernorm", (double)M * D * (l > 0 ? 16 : 14),
+                 vitssl_add_layernorm_bwd_acc(a->dxn, x_l, D, f->mean1[l], f->rstd1[l], f->g1[l], gs_mid, D, gs_in, D,
+                                              l > 0 ? a->dbranch : nullptr, a->dg1[l], a->dbe1[l], M, D, l > 0 ? p : 0.f,
+                                              f->seed, (uint64_t)(l > 0 ? 3 * l - 1 : 0), stream));
     gs = gs_in;
   }
   return 0;

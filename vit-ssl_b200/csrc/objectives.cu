@@ -72,6 +72,26 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const __nv_bfloat16* __res
   if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
 }
 
+// d(pred) = sign * (grad_out / n): grad_out is a DEVICE scalar (the GradScaler-scaled upstream gradient)
+__global__ void __launch_bounds__(256) l1_loss_bwd_kernel(const __nv_bfloat16* __restrict__ sign,
+                                                          const float* __restrict__ grad_out, float inv_n,
+                                                          __nv_bfloat16* __restrict__ dpred, long long n) {
+  const float s = *grad_out * inv_n;
+  const long long stride = static_cast<long long>(gridDim.x) * 256 * 8;
+  for (long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(sign + i), v);
+      uint4 o;
+      o.x = pack_bf16(v[0] * s, v[1] * s); o.y = pack_bf16(v[2] * s, v[3] * s);
+      o.z = pack_bf16(v[4] * s, v[5] * s); o.w = pack_bf16(v[6] * s, v[7] * s);
+      *reinterpret_cast<uint4*>(dpred + i) = o;
+    } else {
+      for (long long j = i; j < n; ++j) dpred[j] = __float2bfloat16_rn(__bfloat162float(sign[j]) * s);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // row L2 normalisation (F.normalize(dim=1), eps 1e-12): y = x / max(||x||, eps)
 // ---------------------------------------------------------------------------------------
@@ -410,6 +430,19 @@ extern "C" int vitssl_l1_loss_fwd(const void* pred, const float* target, void* s
   return check_launch("l1_loss_fwd");
 }
 
+extern "C" int vitssl_l1_loss_bwd(const void* sign, const float* grad_out, void* dpred, int64_t n,
+                                  cudaStream_t stream) {
+  VITSSL_REQUIRE(sign && grad_out && dpred && n > 0, VITSSL_ERR_ARG, "l1_loss_bwd: bad args");
+  VITSSL_REQUIRE(aligned16(sign) && aligned16(dpred), VITSSL_ERR_ARG, "l1_loss_bwd: 16-byte alignment required");
+  long long blocks = (n / 8 + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  l1_loss_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)sign, grad_out, 1.0f / (float)n,
+                                                           (__nv_bfloat16*)dpred, n);
+  return check_launch("l1_loss_bwd");
+}
+
 extern "C" int vitssl_l2norm_fwd(const void* x, void* y, float* inv_norm, int64_t rows, int64_t D, cudaStream_t stream) {
   VITSSL_REQUIRE(x && y && inv_norm && rows >= 0 && D > 0, VITSSL_ERR_ARG, "l2norm_fwd: bad args");
   if (rows == 0) return 0;
@@ -446,26 +479,36 @@ extern "C" int vitssl_dino_loss_fwd(const void* teacher, const void* student, co
                                     float* t_stats, float* s_lse, int64_t G, int64_t V, int64_t B, int64_t K,
                                     float teacher_temp, float student_temp, cudaStream_t stream) {
   VITSSL_REQUIRE(teacher && student && center && loss && t_stats && s_lse, VITSSL_ERR_ARG, "dino_loss_fwd: null pointer");
-  VITSSL_REQUIRE(G >= 1 && G <= 2 && B > 0 && K > 0 && K % 8 == 0, VITSSL_ERR_SHAPE,
-                 "dino_loss_fwd: unsupported G=%lld (1..2) or K=%lld (multiple of 8)", (long long)G, (long long)K);
+  VITSSL_REQUIRE(G >= 1 && G <= DL_MAX_G && B > 0 && K > 0 && K % 8 == 0, VITSSL_ERR_SHAPE,
+                 "dino_loss_fwd: unsupported G=%lld (1..4) or K=%lld (multiple of 8)", (long long)G, (long long)K);
   VITSSL_REQUIRE(teacher_temp > 0.f && student_temp > 0.f, VITSSL_ERR_ARG, "dino_loss_fwd: temperatures must be positive");
   DinoLossArgs a{};
   a.teacher = (const __nv_bfloat16*)teacher; a.student = (const __nv_bfloat16*)student; a.center = center;
   a.loss = loss; a.t_stats = t_stats; a.s_lse = s_lse; a.G = (int)G; a.V = (int)V; a.B = (int)B; a.K = (int)K;
   a.inv_tt = 1.0f / teacher_temp; a.inv_ts = 1.0f / student_temp;
   cudaMemsetAsync(loss, 0, sizeof(float), stream);
-  return G == 1 ? dino_fwd_dispatch_v<1>(a, stream) : dino_fwd_dispatch_v<2>(a, stream);
+  switch (G) {
+    case 1: return dino_fwd_dispatch_v<1>(a, stream);
+    case 2: return dino_fwd_dispatch_v<2>(a, stream);
+    case 3: return dino_fwd_dispatch_v<3>(a, stream);
+    default: return dino_fwd_dispatch_v<4>(a, stream);
+  }
 }
 
 extern "C" int vitssl_dino_loss_bwd(const void* teacher, const void* student, const float* center, const float* t_stats,
                                     const float* s_lse, const float* grad_out, void* dstudent, int64_t G, int64_t V,
                                     int64_t B, int64_t K, float teacher_temp, float student_temp, cudaStream_t stream) {
   VITSSL_REQUIRE(teacher && student && center && t_stats && s_lse && grad_out && dstudent, VITSSL_ERR_ARG, "dino_loss_bwd: null pointer");
-  VITSSL_REQUIRE(G >= 1 && G <= 2 && B > 0 && K > 0 && K % 8 == 0, VITSSL_ERR_SHAPE, "dino_loss_bwd: unsupported shape");
+  VITSSL_REQUIRE(G >= 1 && G <= DL_MAX_G && B > 0 && K > 0 && K % 8 == 0, VITSSL_ERR_SHAPE, "dino_loss_bwd: unsupported shape");
   DinoLossBwdArgs a{};
   a.teacher = (const __nv_bfloat16*)teacher; a.student = (const __nv_bfloat16*)student; a.center = center;
   a.t_stats = t_stats; a.s_lse = s_lse; a.grad_out = grad_out; a.dstudent = (__nv_bfloat16*)dstudent;
   a.G = (int)G; a.V = (int)V; a.B = (int)B; a.K = (int)K; a.inv_tt = 1.0f / teacher_temp; a.inv_ts = 1.0f / student_temp;
   dim3 grid((unsigned)((K / 8 + 255) / 256), (unsigned)B);
-  return G == 1 ? dino_bwd_dispatch_v<1>(a, grid, stream) : dino_bwd_dispatch_v<2>(a, grid, stream);
+  switch (G) {
+    case 1: return dino_bwd_dispatch_v<1>(a, grid, stream);
+    case 2: return dino_bwd_dispatch_v<2>(a, grid, stream);
+    case 3: return dino_bwd_dispatch_v<3>(a, grid, stream);
+    default: return dino_bwd_dispatch_v<4>(a, grid, stream);
+  }
 }

@@ -11,6 +11,10 @@ from .feed_forward import FeedForwardBlock
 from .attention import MultiHeadedAttention, ScaledDotProductAttention
 from .patch_embedding import ConvolutionalPatchEmbedding, ManualPatchEmbedding, DynamicPatchEmbedding
 
+from . import optim as _optim
+
+_optim.register()  # torch.optim.VitsslAdamW: fused AdamW selectable from the reference's config (optim.py)
+
 __all__ = [
     "ViT", "EncoderBlock", "FeedForwardBlock", "MultiHeadedAttention", "ScaledDotProductAttention",
     "ConvolutionalPatchEmbedding", "ManualPatchEmbedding", "DynamicPatchEmbedding",

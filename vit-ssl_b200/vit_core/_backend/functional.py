@@ -7,6 +7,7 @@ GEMM / attention operands and their outputs are bf16 with fp32 accumulation.
 from __future__ import annotations
 
 import math
+import weakref
 from types import SimpleNamespace
 from typing import List, Optional, Sequence
 
@@ -25,6 +26,11 @@ def _cache_of(owner) -> dict:
         c = {}
         object.__setattr__(owner, "_vitssl_cache", c)
     return c
+
+
+# id(param) -> (weakref to the cache dict's owner, key, bf16 destination view): lets the fused
+# optimizer (vit_core/optim.py) write the shadow in its update pass and mark it fresh
+_SHADOW_REG: dict = {}
 
 
 def bf16_shadows(requests):
@@ -49,16 +55,60 @@ def bf16_shadows(requests):
         else:
             buf = torch.empty((rows, cols), device=dev, dtype=torch.bfloat16)
         r = 0
+        views = []
         for p in params:
             pd = p.detach()
             srcs.append(pd if pd.is_contiguous() else pd.contiguous())
             dsts.append(buf[r:r + p.shape[0]])
+            views.append(dsts[-1])
             r += p.shape[0]
-        cache[key] = (buf, sig)
+        cache[key] = (buf, sig, tuple(weakref.ref(p) for p in params))
+        owner_ref = weakref.ref(owner)
+        for p, v in zip(params, views):
+            _SHADOW_REG[id(p)] = (owner_ref, key, v, weakref.ref(p))
         outs.append(buf)
     if srcs:
         ops.multi_cast_bf16(srcs, dsts)
     return outs
+
+
+def shadow_destination(param):
+    """bf16 view that shadows `param` in some module's GEMM-operand cache, or None."""
+    ent = _SHADOW_REG.get(id(param))
+    if ent is None:
+        return None
+    owner, key, view, pref = ent[0](), ent[1], ent[2], ent[3]()
+    if owner is None or pref is not param:
+        _SHADOW_REG.pop(id(param), None)
+        return None
+    cur = owner.__dict__.get("_vitssl_cache", {}).get(key)
+    if cur is None or cur[0].data_ptr() > view.data_ptr() or view.device != param.device or not param.is_contiguous():
+        return None
+    if view.data_ptr() + view.numel() * 2 > cur[0].data_ptr() + cur[0].numel() * 2:
+        return None
+    return view
+
+
+def mark_shadows_fresh(params):
+    """After an in-place update that also wrote the shadows (fused optimizer): re-sign the cache
+    entries of `params` with their current versions so the next forward skips the cast."""
+    seen = set()
+    for p in params:
+        ent = _SHADOW_REG.get(id(p))
+        if ent is None:
+            continue
+        owner = ent[0]()
+        if owner is None or (id(owner), ent[1]) in seen:
+            continue
+        seen.add((id(owner), ent[1]))
+        cache = owner.__dict__.get("_vitssl_cache", {})
+        cur = cache.get(ent[1])
+        if cur is None:
+            continue
+        ps = [r() for r in cur[2]]
+        if any(q is None for q in ps):
+            continue
+        cache[ent[1]] = (cur[0], tuple((q.data_ptr(), q._version) for q in ps), cur[2])
 
 
 def _new_seed() -> int:
@@ -209,17 +259,16 @@ class _EncoderStackFn(torch.autograd.Function):
             # data parallel: the stack runs as a few layer chunks, and each chunk's gradient slice
             # starts its all-reduce on the communication stream while the next chunk computes
             sync = dp.sync_for(ctx.params) if all(ctx.needs_input_grad[2:]) else None
+            run = ops.EncoderStackBackward(st, g)
+            n_chunks = min(L, DP_STACK_CHUNKS) if sync is not None else 1
+            bounds = [round(i * L / n_chunks) for i in range(n_chunks + 1)]
+            for c in reversed(range(n_chunks)):
+                run.run(bounds[c], bounds[c + 1])
+                if sync is not None:
+                    sync.prereduce(run.flat_slice(bounds[c], bounds[c + 1]), ctx.params[12 * bounds[c]:12 * bounds[c + 1]])
             if sync is not None:
-                dx, gr = ops.encoder_stack_bwd(st, g, n_chunks=min(L, DP_STACK_CHUNKS),
-                                               on_chunk=lambda flat, lo, hi: sync.prereduce(flat, ctx.params[12 * lo:12 * hi]))
                 sync.join()  # only the last chunk's all-reduce is still in flight here
-            else:
-                dx, gr = ops.encoder_stack_bwd(st, g)
-            grads = []
-            for l in range(L):
-                wq = gr["dwqkv"][l]
-                grads += [wq[:D], wq[D:2 * D], wq[2 * D:], gr["dwo"][l], gr["dw1"][l], gr["db1"][l], gr["dw2"][l],
-                          gr["db2"][l], gr["dg1"][l], gr["dbe1"][l], gr["dg2"][l], gr["dbe2"][l]]
+            dx, grads = run.dx, run.param_grads()
             for i, need in enumerate(ctx.needs_input_grad[2:]):
                 if not need:
                     grads[i] = None
@@ -264,11 +313,74 @@ class _EncoderStackFn(torch.autograd.Function):
                                                            seed=seed, offset=max(3 * l - 1, 0))
             grads[12 * l:12 * l + 12] = [dWqkv[:D], dWqkv[D:2 * D], dWqkv[2 * D:], dWo, dW1, db1, dW2, db2,
                                          dg1, dbe1, dg2, dbe2]
+        # data parallel: this path pre-reduces its contributions exactly like the fused one, so a
+        # parameter shared by a fused node and a per-op node (DINO global / local passes with
+        # different S) is averaged once per contribution and the hooks skip it consistently
+        sync = dp.sync_for(params) if all(ctx.needs_input_grad[2:]) else None
+        if sync is not None:
+            flat = torch.cat([g_.reshape(-1) for g_ in grads])
+            sync.prereduce(flat, params)
+            sync.join()
+            off = 0
+            for i, g_ in enumerate(grads):
+                grads[i] = flat[off:off + g_.numel()].view(g_.shape)
+                off += g_.numel()
         for i, need in enumerate(ctx.needs_input_grad[2:]):
             if not need:
                 grads[i] = None
         dx = gs.view(B, S, D) if ctx.needs_input_grad[0] else None
         return (dx, None, *grads)
+
+
+class _EncoderStackMultiFn(torch.autograd.Function):
+    """Several token batches (different B and S) through the SAME L blocks as ONE autograd node, e.g.
+    DINO's global-crop and local-crop student passes (ssl/dino/model.py:117-118). Every pass's
+    parameter gradients accumulate into one zeroed layer-major buffer on the C side, so autograd
+    never adds per-parameter gradients of the two passes (149 tiny launches per step before), and
+    under data parallelism a layer chunk is all-reduced once, after all passes contributed to it."""
+
+    @staticmethod
+    def forward(ctx, meta, n_in, *args):
+        xs, params = args[:n_in], args[n_in:]
+        need_grad = any(ctx.needs_input_grad)
+        p = meta.p if meta.training else 0.0
+        outs, states = [], []
+        for x in xs:
+            x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+            seed = _new_seed() if p > 0 else 0
+            out, st = ops.encoder_stack_fwd(x, meta.weights, params, meta.H, p, seed, need_grad)
+            outs.append(out)
+            states.append(st)
+        if need_grad:
+            ctx.states, ctx.meta, ctx.params, ctx.n_in = states, meta, params, n_in
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        states, ctx.states = ctx.states, None
+        n_in, L = ctx.n_in, ctx.meta.L
+        runs, flat = [], None
+        for st, g in zip(states, gouts):
+            g = g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()
+            r = ops.EncoderStackBackward(st, g, flat=flat)
+            flat = r.flat
+            runs.append(r)
+        sync = dp.sync_for(ctx.params) if all(ctx.needs_input_grad[2 + n_in:]) else None
+        n_chunks = min(L, DP_STACK_CHUNKS) if sync is not None else 1
+        bounds = [round(i * L / n_chunks) for i in range(n_chunks + 1)]
+        for c in reversed(range(n_chunks)):
+            for r in runs:
+                r.run(bounds[c], bounds[c + 1])
+            if sync is not None:
+                sync.prereduce(runs[0].flat_slice(bounds[c], bounds[c + 1]), ctx.params[12 * bounds[c]:12 * bounds[c + 1]])
+        if sync is not None:
+            sync.join()
+        grads = runs[0].param_grads()
+        for i, need in enumerate(ctx.needs_input_grad[2 + n_in:]):
+            if not need:
+                grads[i] = None
+        dxs = [r.dx if ctx.needs_input_grad[2 + i] else None for i, r in enumerate(runs)]
+        return (None, None, *dxs, *grads)
 
 
 def block_params(blk) -> list:
@@ -306,6 +418,30 @@ def encoder_stack(blocks: Sequence, x: torch.Tensor, return_attn: bool = False):
     if return_attn:
         return out[0], out[1]
     return out, None
+
+
+def encoder_stack_multi(blocks: Sequence, xs: Sequence[torch.Tensor]):
+    """`encoder_stack` for several token batches sharing the blocks; returns a list of outputs."""
+    blocks = list(blocks)
+    xs = list(xs)
+    H = blocks[0].self_attention.num_heads if blocks else 0
+    if len(xs) < 2 or not blocks or not all(ops.encoder_stack_supported(x.shape[1], x.shape[2], H) for x in xs):
+        return [encoder_stack(blocks, x)[0] for x in xs]
+    reqs = []
+    for blk in blocks:
+        a, f = blk.self_attention, blk.feed_forward
+        reqs += [(a, "wqkv", [a.w_query.weight, a.w_key.weight, a.w_value.weight]),
+                 (a, "wo", [a.final_linear.weight]),
+                 (f, "w1", [f.linear_in.weight]),
+                 (f, "w2", [f.linear_out.weight])]
+    sh = bf16_shadows(reqs)
+    b0 = blocks[0]
+    meta = SimpleNamespace(L=len(blocks), H=H, p=float(b0.drop1.p), training=bool(b0.training),
+                           weights=[tuple(sh[4 * i:4 * i + 4]) for i in range(len(blocks))])
+    params = []
+    for blk in blocks:
+        params += block_params(blk)
+    return list(_EncoderStackMultiFn.apply(meta, len(xs), *xs, *params))
 
 
 # ----------------------------------------------------------------------------------------
@@ -529,11 +665,19 @@ def layer_norm(x, ln_module):
 # patch embedding: im2col + projection GEMM + token assembly
 # (patch_embedding.py:50-63, 90-96, 122-128; ssl/simmim/model.py:43-49)
 # ----------------------------------------------------------------------------------------
+def _as_image(img):
+    """Images reach the kernels as contiguous fp32 [B,C,H,W] (ToTensor output, what the reference's
+    loaders yield) or as raw uint8 bytes, which the kernels scale by 1/255 themselves (§8(f)3)."""
+    if img.dtype == torch.uint8:
+        return img if img.is_contiguous() else img.contiguous()
+    return img if (img.dtype == torch.float32 and img.is_contiguous()) else img.float().contiguous()
+
+
 class _EmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, meta, weight, bias, cls, pos, mask_token):
         p = meta.patch
-        img = img if (img.dtype == torch.float32 and img.is_contiguous()) else img.float().contiguous()
+        img = _as_image(img)
         B, C, Hh, Ww = img.shape
         N = (Hh // p) * (Ww // p)
         D = weight.shape[0]
@@ -561,16 +705,104 @@ class _EmbedFn(torch.autograd.Function):
         has_cls = cshape is not None
         dproj, dpos, dmt = ops.embed_tokens_bwd(g, meta.mask_u8 if mshape is not None else None, B, N, D,
                                                 has_cls, mshape is not None)
-        dW = ops.gemm(dproj, patches, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1).view(wshape)
-        db = ops.colsum_bf16(dproj)
+        try:  # bias gradient from the weight-gradient kernel (ones-operand MMA) where the shape allows
+            dW, db = ops.gemm_rowsum(dproj, patches, a_mn=True, b_mn=True, split_k=-1)
+        except ops._l.VitsslError:
+            dW = ops.gemm(dproj, patches, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
+            db = ops.colsum_bf16(dproj)
         dcls = dpos[0].reshape(cshape).clone() if has_cls else None
-        return (None, None, dW, db, dcls, dpos.view(pshape), None if dmt is None else dmt.view(mshape))
+        return (None, None, dW.view(wshape), db, dcls, dpos.view(pshape), None if dmt is None else dmt.view(mshape))
 
 
 def embed_patches(img, owner, weight, bias, cls, pos, patch, mask_u8=None, mask_token=None):
+    """[B,C,H,W] image -> fp32 tokens [B, N(+1), D] = (CLS | mask_token | projection) + pos.
+    Shape errors surface here as ValueError, like the reference's broadcast failure in
+    `x += positional_embedding` (patch_embedding.py:63,95; ssl/simmim/model.py:49) — the kernels
+    index `pos` by token and would otherwise read out of bounds."""
+    if img.dim() != 4:
+        raise ValueError(f"expected images [B,C,H,W], got {tuple(img.shape)}")
+    B, C, Hh, Ww = img.shape
+    D = weight.shape[0]
+    if Hh % patch or Ww % patch:
+        raise ValueError(f"Image dimensions H={Hh}, W={Ww} must be divisible by patch_size={patch}")
+    if C * patch * patch != weight.numel() // D:
+        raise ValueError(f"patch features C*p*p = {C * patch * patch} do not match the projection ({weight.numel() // D})")
+    S = (Hh // patch) * (Ww // patch) + (1 if cls is not None else 0)
+    if pos.numel() != S * D:
+        raise ValueError(f"positional embedding {tuple(pos.shape)} does not match {S} tokens of width {D} "
+                         f"(image {Hh}x{Ww}, patch {patch})")
+    if cls is not None and cls.numel() != D:
+        raise ValueError(f"cls_token {tuple(cls.shape)} does not have {D} features")
+    if mask_token is not None and mask_token.numel() != D:
+        raise ValueError(f"mask_token {tuple(mask_token.shape)} does not have {D} features")
     (w_bf16,) = bf16_shadows([(owner, "wproj", [weight])])
     meta = SimpleNamespace(patch=int(patch), w_bf16=w_bf16, mask_u8=mask_u8)
     return _EmbedFn.apply(img, meta, weight, bias, cls, pos, mask_token)
+
+
+# ----------------------------------------------------------------------------------------
+# bicubic resize of the positional-embedding grid (patch_embedding.py:26-48) as a sparse row
+# interpolation: a 16-tap (index, weight) table per output token, built once per grid pair with
+# torch's upsample_bicubic2d arithmetic (align_corners=False: src = (dst + 0.5) * in/out - 0.5,
+# cubic-convolution coefficients with A = -0.75, border indices clamped). Row 0 (CLS) passes through.
+# ----------------------------------------------------------------------------------------
+_BICUBIC_TABLES: dict = {}
+
+
+def bicubic_tables(in_h, in_w, out_h, out_w, device, with_cls=True):
+    key = (in_h, in_w, out_h, out_w, str(device), with_cls)
+    hit = _BICUBIC_TABLES.get(key)
+    if hit is not None:
+        return hit
+    A = -0.75
+
+    def axis(n_in, n_out):
+        scale = n_in / n_out
+        idx, wts = [], []
+        for o in range(n_out):
+            src = scale * (o + 0.5) - 0.5
+            f = math.floor(src)
+            t = src - f
+            c1 = lambda x: ((A + 2.0) * x - (A + 3.0)) * x * x + 1.0
+            c2 = lambda x: ((A * x - 5.0 * A) * x + 8.0 * A) * x - 4.0 * A
+            wts.append([c2(t + 1.0), c1(t), c1(1.0 - t), c2(2.0 - t)])
+            idx.append([min(max(f - 1 + k, 0), n_in - 1) for k in range(4)])
+        return idx, wts
+
+    iy, wy = axis(in_h, out_h)
+    ix, wx = axis(in_w, out_w)
+    off = 1 if with_cls else 0
+    idx, w = [], []
+    if with_cls:
+        idx.append([0] * 16)
+        w.append([1.0] + [0.0] * 15)
+    for oy in range(out_h):
+        for ox in range(out_w):
+            idx.append([off + iy[oy][a] * in_w + ix[ox][b] for a in range(4) for b in range(4)])
+            w.append([wy[oy][a] * wx[ox][b] for a in range(4) for b in range(4)])
+    out = (torch.tensor(idx, dtype=torch.int32, device=device), torch.tensor(w, dtype=torch.float32, device=device))
+    _BICUBIC_TABLES[key] = out
+    return out
+
+
+class _InterpRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, idx, w):
+        s2 = src if (src.dtype == torch.float32 and src.is_contiguous()) else src.float().contiguous()
+        ctx.tables, ctx.n_in, ctx.dt = (idx, w), s2.shape[0], src.dtype
+        return ops.interp_rows_fwd(s2, idx, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, w = ctx.tables
+        g = g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()
+        return ops.interp_rows_bwd(g, idx, w, ctx.n_in).to(ctx.dt), None, None
+
+
+def interpolate_pos_embedding(pos, grid_in, grid_out):
+    """pos [1, 1 + gh*gw, D] (CLS row first) -> [1, 1 + oh*ow, D], bicubic over the patch grid."""
+    idx, w = bicubic_tables(grid_in[0], grid_in[1], grid_out[0], grid_out[1], pos.device)
+    return _InterpRowsFn.apply(pos.reshape(-1, pos.shape[-1]), idx, w).unsqueeze(0)
 
 
 # ----------------------------------------------------------------------------------------
@@ -609,7 +841,8 @@ class _L1LossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         (sign,) = ctx.saved
-        return (sign * (go / ctx.n).to(sign.dtype)).to(ctx.dt), None
+        d = ops.l1_loss_bwd(sign, go)  # one pass: sign * (go / n), go read on the device
+        return (d if ctx.dt == torch.bfloat16 else d.to(ctx.dt)), None
 
 
 def l1_loss(pred, target):

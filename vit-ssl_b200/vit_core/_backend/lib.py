@@ -60,6 +60,15 @@ SIGNATURES["vitssl_center_ema"] = "ppplff" + "s"
 SIGNATURES["vitssl_dino_loss_fwd"] = "pppppp" + "llll" + "ff" + "s"
 SIGNATURES["vitssl_dino_loss_bwd"] = "ppppppp" + "llll" + "ff" + "s"
 
+SIGNATURES["vitssl_im2col_u8_bf16"] = SIGNATURES["vitssl_im2col_bf16"]
+SIGNATURES["vitssl_gather_patches_u8_f32"] = SIGNATURES["vitssl_gather_patches_f32"]
+SIGNATURES["vitssl_interp_rows_fwd"] = "pppp" + "lll" + "s"
+SIGNATURES["vitssl_interp_rows_bwd"] = "pppp" + "llll" + "s"
+SIGNATURES["vitssl_l1_loss_bwd"] = "pppl" + "s"
+SIGNATURES["vitssl_adamw_step"] = "ppppppp" + "i" + "fffff" + "pp" + "s"
+SIGNATURES["vitssl_profile_read"] = "lplpp"
+SIGNATURES["vitssl_multi_ema_shadow"] = "ppppifs"
+
 _lib = None
 
 
@@ -83,6 +92,8 @@ def _load():
     lib.vitssl_num_sms.restype = ctypes.c_int
     lib.vitssl_launch_count.restype = ctypes.c_int64
     lib.vitssl_launch_count.argtypes = [ctypes.c_int]
+    lib.vitssl_profile_begin.restype = ctypes.c_int
+    lib.vitssl_profile_end.restype = ctypes.c_int64
     lib.vitssl_randperm_bits.restype = ctypes.c_int
     lib.vitssl_randperm_bits.argtypes = [ctypes.c_int64]
     lib.vitssl_randperm_offset_per_call.restype = ctypes.c_int64
@@ -134,6 +145,24 @@ def call(name: str, *args):
     rc = getattr(l, name)(*args)
     if rc != 0:
         raise VitsslError(f"{name} failed ({rc}): {l.vitssl_last_error().decode()}")
+
+
+def profile_begin() -> None:
+    """Open a per-launch profile of the C-sequenced paths (csrc/api.cu, ProfScope)."""
+    _load().vitssl_profile_begin()
+
+
+def profile_collect():
+    """Close the profile; returns [(kind, ms, algorithmic work)] — waits for the device."""
+    l = _load()
+    n = int(l.vitssl_profile_end())
+    out = []
+    kind = ctypes.create_string_buffer(64)
+    work, ms = ctypes.c_double(), ctypes.c_float()
+    for i in range(n):
+        call("vitssl_profile_read", i, ctypes.addressof(kind), 64, ctypes.addressof(work), ctypes.addressof(ms))
+        out.append((kind.value.decode(), float(ms.value), float(work.value)))
+    return out
 
 
 def launch_count(reset: bool = False) -> int:

@@ -296,6 +296,21 @@ def multi_ema(teacher, student, momentum):
             len(teacher), float(momentum), _l.stream_ptr())
 
 
+def multi_ema_shadow(teacher, student, shadows, momentum):
+    """`multi_ema` that also writes each teacher tensor's bf16 shadow (shadows[i] or None)."""
+    import ctypes
+    if not teacher:
+        return
+    _l.ensure_device()
+    for t, s_, sh in zip(teacher, student, shadows):
+        assert t.dtype == torch.float32 and s_.dtype == torch.float32
+        assert t.is_contiguous() and s_.is_contiguous() and t.numel() == s_.numel()
+        assert sh is None or (sh.dtype == torch.bfloat16 and sh.is_contiguous() and sh.numel() == t.numel())
+    a, b, c, n = _ptr_array(teacher), _ptr_array(student), _ptr_array(shadows), _numel_array(teacher)
+    _l.call("vitssl_multi_ema_shadow", ctypes.addressof(a), ctypes.addressof(b), ctypes.addressof(c),
+            ctypes.addressof(n), len(teacher), float(momentum), _l.stream_ptr())
+
+
 def colsum_bf16(x):
     """x: bf16 [rows, cols] (unit inner stride) -> fp32 [cols]."""
     _l.ensure_device()
@@ -306,22 +321,45 @@ def colsum_bf16(x):
 
 
 def im2col_bf16(img, p):
+    """img: fp32 [B,C,H,W], or raw uint8 image bytes (value = byte / 255, torchvision ToTensor)."""
     _l.ensure_device()
-    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4
+    assert img.dtype in (torch.float32, torch.uint8) and img.is_contiguous() and img.dim() == 4
     B, C, H, W = img.shape
     out = torch.empty((B * (H // p) * (W // p), C * p * p), device=img.device, dtype=torch.bfloat16)
-    _l.call("vitssl_im2col_bf16", _p(img), _p(out), B, C, H, W, p, _l.stream_ptr())
+    name = "vitssl_im2col_bf16" if img.dtype == torch.float32 else "vitssl_im2col_u8_bf16"
+    _l.call(name, _p(img), _p(out), B, C, H, W, p, _l.stream_ptr())
     return out
 
 
 def gather_patches_f32(img, rows_idx, p):
     _l.ensure_device()
-    assert img.dtype == torch.float32 and img.is_contiguous() and rows_idx.dtype == torch.int32
+    assert img.dtype in (torch.float32, torch.uint8) and img.is_contiguous() and rows_idx.dtype == torch.int32
     B, C, H, W = img.shape
     out = torch.empty((rows_idx.numel(), C * p * p), device=img.device, dtype=torch.float32)
-    _l.call("vitssl_gather_patches_f32", _p(img), _p(rows_idx), _p(out), rows_idx.numel(), C, H, W, p,
-            _l.stream_ptr())
+    name = "vitssl_gather_patches_f32" if img.dtype == torch.float32 else "vitssl_gather_patches_u8_f32"
+    _l.call(name, _p(img), _p(rows_idx), _p(out), rows_idx.numel(), C, H, W, p, _l.stream_ptr())
     return out
+
+
+def interp_rows_fwd(src, idx, w):
+    """dst[i,:] = sum_t w[i,t] * src[idx[i,t],:]; src fp32 [n_in, D], idx int32 / w fp32 [n_out, taps]."""
+    _l.ensure_device()
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 2
+    assert idx.dtype == torch.int32 and w.dtype == torch.float32 and idx.shape == w.shape and idx.is_contiguous() and w.is_contiguous()
+    n_out, taps = idx.shape
+    dst = torch.empty((n_out, src.shape[1]), device=src.device, dtype=torch.float32)
+    _l.call("vitssl_interp_rows_fwd", _p(src), _p(idx), _p(w), _p(dst), n_out, src.shape[1], taps, _l.stream_ptr())
+    return dst
+
+
+def interp_rows_bwd(ddst, idx, w, n_in):
+    _l.ensure_device()
+    assert ddst.dtype == torch.float32 and ddst.is_contiguous()
+    n_out, taps = idx.shape
+    dsrc = torch.empty((n_in, ddst.shape[1]), device=ddst.device, dtype=torch.float32)
+    _l.call("vitssl_interp_rows_bwd", _p(ddst), _p(idx), _p(w), _p(dsrc), n_in, n_out, ddst.shape[1], taps,
+            _l.stream_ptr())
+    return dsrc
 
 
 RANDPERM_MAX_N = 1024
@@ -399,6 +437,40 @@ def l1_loss_fwd(pred, target, want_sign=True):
     loss = torch.empty((), device=pred.device, dtype=torch.float32)
     _l.call("vitssl_l1_loss_fwd", _p(pred), _p(target), _p(sign), _p(loss), pred.numel(), _l.stream_ptr())
     return loss, sign
+
+
+def l1_loss_bwd(sign, grad_out):
+    """d(pred) = sign * grad_out / n, grad_out a device scalar (any float dtype)."""
+    _l.ensure_device()
+    go = grad_out.reshape(()).to(torch.float32).contiguous()
+    dpred = torch.empty_like(sign)
+    _l.call("vitssl_l1_loss_bwd", _p(sign), _p(go), _p(dpred), sign.numel(), _l.stream_ptr())
+    return dpred
+
+
+def adamw_step(params, grads, exp_avgs, exp_avg_sqs, shadows, steps, lr, beta1, beta2, eps, weight_decay,
+               grad_scale=None, found_inf=None):
+    """Fused multi-tensor AdamW (csrc/optimizer.cu). All lists hold contiguous fp32 CUDA tensors of
+    equal sizes per index; shadows[i] is a contiguous bf16 destination or None; steps[i] a 0-dim fp32
+    device counter. grad_scale / found_inf: 0-dim fp32 device tensors or None."""
+    import ctypes
+    if not params:
+        return
+    _l.ensure_device()
+    for p_, g_, m_, v_ in zip(params, grads, exp_avgs, exp_avg_sqs):
+        assert p_.dtype == torch.float32 and g_.dtype == torch.float32 and p_.is_contiguous() and g_.is_contiguous()
+        assert m_.is_contiguous() and v_.is_contiguous() and p_.numel() == g_.numel() == m_.numel() == v_.numel()
+    sh = None
+    if shadows is not None and any(t is not None for t in shadows):
+        for p_, t in zip(params, shadows):
+            assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() == p_.numel())
+        sh = _ptr_array(shadows)
+    a, g, m, v, st, n = (_ptr_array(params), _ptr_array(grads), _ptr_array(exp_avgs), _ptr_array(exp_avg_sqs),
+                         _ptr_array(steps), _numel_array(params))
+    _l.call("vitssl_adamw_step", ctypes.addressof(a), ctypes.addressof(g), ctypes.addressof(m), ctypes.addressof(v),
+            ctypes.addressof(sh) if sh is not None else None, ctypes.addressof(st), ctypes.addressof(n), len(params),
+            float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), _p(grad_scale), _p(found_inf),
+            _l.stream_ptr())
 
 
 def l2norm_fwd(x):
@@ -506,7 +578,7 @@ def _list_ptrs(ts):
 
 
 def encoder_stack_supported(S, D, H):
-    return PROFILE is None and D == H * 64 and D % 8 == 0 and attention_supported(S, S, 64)
+    return D == H * 64 and D % 8 == 0 and attention_supported(S, S, 64)
 
 
 class EncoderStackState:
@@ -573,50 +645,84 @@ def encoder_stack_last_qkv(st):
     return qkv[qkv.shape[0] - 1].view(B, S, 3 * D)
 
 
+_STACK_GRAD_SHAPES = lambda D, F_: (("dwqkv", (3 * D, D)), ("dwo", (D, D)), ("dw1", (F_, D)), ("db1", (F_,)),
+                                    ("dw2", (D, F_)), ("db2", (D,)), ("dg1", (D,)), ("dbe1", (D,)), ("dg2", (D,)),
+                                    ("dbe2", (D,)))
+
+
+class EncoderStackBackward:
+    """Backward of one `encoder_stack_fwd` call, runnable as descending layer ranges.
+
+    Every parameter gradient of the stack lives in ONE zeroed fp32 buffer, layer-major: the C side
+    accumulates into it (split-K TMA reduce-adds, fused bias column sums, LayerNorm dgamma/dbeta), so
+    a single fill replaces ~125 per-kernel memsets per step, a range of layers is one contiguous
+    slice (data parallelism all-reduces it while the next range computes), and a second pass over
+    the same blocks (`flat=` given) simply keeps accumulating."""
+
+    def __init__(self, st, gout, flat=None):
+        B, S, D, H, F_, L = st.dims
+        M = B * S
+        dev = gout.device
+        bf, f32 = torch.bfloat16, torch.float32
+        self.st, self.L, self.D = st, L, D
+        self.dx = torch.empty((B, S, D), device=dev, dtype=f32)
+        tmp_d = torch.empty((3, M, D), device=dev, dtype=bf)        # dbranch, dxn, dctx
+        du = torch.empty((M, F_), device=dev, dtype=bf)
+        dqkv = torch.empty((M, 3 * D), device=dev, dtype=bf)
+        gs = torch.empty((2, M, D), device=dev, dtype=f32)
+        shapes = _STACK_GRAD_SHAPES(D, F_)
+        self.per_layer = sum(int(torch.Size(shp).numel()) for _, shp in shapes)
+        if flat is None:
+            flat = torch.zeros((L * self.per_layer,), device=dev, dtype=f32)
+        assert flat.numel() == L * self.per_layer
+        self.flat = flat
+        g = {k: [] for k, _ in shapes}
+        for l in range(L):
+            off = l * self.per_layer
+            for k, shp in shapes:
+                n = int(torch.Size(shp).numel())
+                g[k].append(flat[off:off + n].view(shp))
+                off += n
+        self.g = g
+        b = _EncBwdArgs()
+        b.fwd = _ct.pointer(st.args)
+        b.gout, b.dx = _p(gout), _p(self.dx)
+        b.dbranch, b.dxn, b.dctx = _p(tmp_d[0]), _p(tmp_d[1]), _p(tmp_d[2])
+        b.du, b.dqkv = _p(du), _p(dqkv)
+        b.gs[0], b.gs[1] = _p(gs[0]), _p(gs[1])
+        arrays = {name: (_ct.c_void_p * L)(*[_p(t) for t in views]) for name, views in g.items()}
+        for name, arr in arrays.items():
+            setattr(b, name, _ct.cast(arr, _PP))
+        self.args = b
+        self.keep = (gout, tmp_d, du, dqkv, gs, arrays)
+
+    def run(self, l_begin, l_end):
+        self.args.l_begin, self.args.l_end = int(l_begin), int(l_end)
+        _l.call("vitssl_encoder_stack_bwd", _ct.addressof(self.args), _l.stream_ptr())
+
+    def flat_slice(self, l_begin, l_end):
+        return self.flat[l_begin * self.per_layer:l_end * self.per_layer]
+
+    def param_grads(self):
+        """Gradient views in functional.block_params order (12 per layer)."""
+        D, g, out = self.D, self.g, []
+        for l in range(self.L):
+            wq = g["dwqkv"][l]
+            out += [wq[:D], wq[D:2 * D], wq[2 * D:], g["dwo"][l], g["dw1"][l], g["db1"][l], g["dw2"][l],
+                    g["db2"][l], g["dg1"][l], g["dbe1"][l], g["dg2"][l], g["dbe2"][l]]
+        return out
+
+
 def encoder_stack_bwd(st, gout, n_chunks=1, on_chunk=None):
     """gout fp32 [B,S,D] contiguous -> (dx fp32 [B,S,D], per-layer gradient views dict name -> list of L).
-
     The backward may run as `n_chunks` C calls over descending layer ranges; after each one
-    `on_chunk(flat_slice, l_lo, l_hi)` is called with the contiguous fp32 slice that holds every
-    parameter gradient of those layers (data parallelism starts their all-reduce there, while the
-    next chunk computes)."""
-    B, S, D, H, F_, L = st.dims
-    M = B * S
-    dev = gout.device
-    bf, f32 = torch.bfloat16, torch.float32
-    dx = torch.empty((B, S, D), device=dev, dtype=f32)
-    tmp_d = torch.empty((3, M, D), device=dev, dtype=bf)        # dbranch, dxn, dctx
-    du = torch.empty((M, F_), device=dev, dtype=bf)
-    dqkv = torch.empty((M, 3 * D), device=dev, dtype=bf)
-    gs = torch.empty((2, M, D), device=dev, dtype=f32)
-    # every parameter gradient of the stack lives in ONE zeroed fp32 buffer, layer-major: the C side
-    # accumulates into it (split-K TMA reduce-adds, column sums, LayerNorm dgamma/dbeta), so a
-    # single fill replaces ~125 per-kernel memsets per step, and a range of layers is one slice
-    shapes = (("dwqkv", (3 * D, D)), ("dwo", (D, D)), ("dw1", (F_, D)), ("db1", (F_,)), ("dw2", (D, F_)),
-              ("db2", (D,)), ("dg1", (D,)), ("dbe1", (D,)), ("dg2", (D,)), ("dbe2", (D,)))
-    per_layer = sum(int(torch.Size(shp).numel()) for _, shp in shapes)
-    flat = torch.zeros((L * per_layer,), device=dev, dtype=f32)
-    g = {k: [] for k, _ in shapes}
-    for l in range(L):
-        off = l * per_layer
-        for k, shp in shapes:
-            n = int(torch.Size(shp).numel())
-            g[k].append(flat[off:off + n].view(shp))
-            off += n
-    b = _EncBwdArgs()
-    b.fwd = _ct.pointer(st.args)
-    b.gout, b.dx = _p(gout), _p(dx)
-    b.dbranch, b.dxn, b.dctx = _p(tmp_d[0]), _p(tmp_d[1]), _p(tmp_d[2])
-    b.du, b.dqkv = _p(du), _p(dqkv)
-    b.gs[0], b.gs[1] = _p(gs[0]), _p(gs[1])
-    arrays = {name: (_ct.c_void_p * L)(*[_p(t) for t in views]) for name, views in g.items()}
-    for name, arr in arrays.items():
-        setattr(b, name, _ct.cast(arr, _PP))
+    `on_chunk(flat_slice, l_lo, l_hi)` is called with that range's contiguous gradient slice."""
+    run = EncoderStackBackward(st, gout)
+    L = run.L
     n_chunks = max(1, min(int(n_chunks), L))
     bounds = [round(i * L / n_chunks) for i in range(n_chunks + 1)]
     for c in reversed(range(n_chunks)):
-        b.l_begin, b.l_end = bounds[c], bounds[c + 1]
-        _l.call("vitssl_encoder_stack_bwd", _ct.addressof(b), _l.stream_ptr())
+        run.run(bounds[c], bounds[c + 1])
         if on_chunk is not None:
-            on_chunk(flat[bounds[c] * per_layer:bounds[c + 1] * per_layer], bounds[c], bounds[c + 1])
-    return dx, g
+            on_chunk(run.flat_slice(bounds[c], bounds[c + 1]), bounds[c], bounds[c + 1])
+    return run.dx, run.g

@@ -6,7 +6,6 @@ in the GEMM epilogue; CLS / positional embedding are added by the token-assembly
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ._backend import functional as Fb
 from ._backend import eager
@@ -30,15 +29,16 @@ class DynamicPatchEmbedding(nn.Module):
         self.cls_token = nn.Parameter(torch.rand(1, 1, embed_dim))
         self.positional_embedding = nn.Parameter(torch.rand(1, self.num_patches + 1, embed_dim))
 
+    @eager
     def interpolate_pos_encoding(self, x, w, h):
+        """Positional embedding for a (w x h) patch grid: the trained one, or its patch part resized
+        bicubically (align_corners=False) with the CLS row passed through (patch_embedding.py:26-48).
+        The resize runs as a 16-tap row-interpolation kernel with precomputed tables, forward and
+        backward, instead of F.interpolate on a permuted copy."""
         npatch = x.shape[1] if torch.is_tensor(x) else int(x)
         if npatch == self.num_patches and w == h:
             return self.positional_embedding
-        dim = self.positional_embedding.shape[-1]
-        cls_pos = self.positional_embedding[:, :1]
-        grid = self.positional_embedding[:, 1:].reshape(1, self.grid_size[0], self.grid_size[1], dim)
-        grid = F.interpolate(grid.permute(0, 3, 1, 2), size=(w, h), mode="bicubic")
-        return torch.cat((cls_pos, grid.permute(0, 2, 3, 1).reshape(1, -1, dim)), dim=1)
+        return Fb.interpolate_pos_embedding(self.positional_embedding, self.grid_size, (w, h))
 
     @eager
     def forward(self, x):
@@ -48,8 +48,7 @@ class DynamicPatchEmbedding(nn.Module):
                 f"Input image dimensions ({height}x{width}) must be divisible by patch size ({self.patch_size})."
             )
         gh, gw = height // self.patch_size, width // self.patch_size
-        with torch.autocast(device_type="cuda", enabled=False):
-            pos = self.interpolate_pos_encoding(gh * gw, gh, gw)
+        pos = self.interpolate_pos_encoding(gh * gw, gh, gw)
         return Fb.embed_patches(x, self, self.proj.weight, self.proj.bias, self.cls_token, pos, self.patch_size)
 
 

@@ -19,9 +19,23 @@ class DINOLoss(nn.Module):
 
     @eager
     def forward(self, teacher_output, student_output, center):
-        if teacher_output.dim() != 3 or student_output.dim() != 3:
+        """teacher [G, *rest, K], student [V, *rest, K] (the trainer passes [G,B,K] / [V,B,K],
+        dino_trainer.py:89-98; 2-D inputs are the reference's all-pairs-across-rows case, i.e. rest
+        = ()), center broadcastable to [K]. Any number of student views: the factorised loss is
+        additive over groups of views, so more than 12 are processed as several kernel calls."""
+        t, s = teacher_output, student_output
+        if t.dim() < 2 or s.dim() != t.dim() or t.shape[1:] != s.shape[1:]:
             raise ValueError(
-                "DINOLoss expects teacher [G,B,K] and student [V,B,K] (as produced by the trainer, "
-                f"dino_trainer.py:89-98); got {tuple(teacher_output.shape)} / {tuple(student_output.shape)}"
-            )
-        return Fb.dino_loss(teacher_output, student_output, center, self.teacher_temp, self.student_temp)
+                "DINOLoss expects teacher [G,...,K] and student [V,...,K] with equal trailing dims; "
+                f"got {tuple(t.shape)} / {tuple(s.shape)}")
+        if center.numel() != t.shape[-1]:
+            raise ValueError(f"center {tuple(center.shape)} does not match the head width {t.shape[-1]}")
+        if t.shape[0] > 4:
+            raise ValueError(f"DINOLoss kernels support up to 4 teacher views, got {t.shape[0]}")
+        K = t.shape[-1]
+        t3, s3 = t.reshape(t.shape[0], -1, K), s.reshape(s.shape[0], -1, K)
+        loss = None
+        for v0 in range(0, s3.shape[0], 12):
+            part = Fb.dino_loss(t3, s3[v0:v0 + 12], center, self.teacher_temp, self.student_temp)
+            loss = part if loss is None else loss + part
+        return loss

@@ -40,6 +40,14 @@ class ViTBackbone(nn.Module):
             return cls, attn_probs
         return cls
 
+    @eager
+    def forward_views(self, crops):
+        """CLS features of several crop batches of different resolution (model.py:117-118 runs the
+        backbone once per resolution): one autograd node over all of them, rows concatenated in order."""
+        tokens = [self.patch_embedding(c) for c in crops]
+        outs = Fb.encoder_stack_multi(self.encoder_blocks, tokens)
+        return torch.cat([o[:, 0] for o in outs], dim=0)
+
 
 class DINOViT(nn.Module):
     def __init__(self, num_blocks: int, input_shape, embed_dim: int, patch_size: int, num_heads: int = 8,
@@ -84,12 +92,12 @@ class DINOViT(nn.Module):
     def forward(self, multi_crop_views: List[torch.Tensor], num_global_views: int):
         dp.maybe_attach(self)
         global_crops = torch.cat(multi_crop_views[:num_global_views], dim=0)
-        feats = [self.student_backbone(global_crops)]
+        crops = [global_crops]
         if len(multi_crop_views) > num_global_views:
-            local_crops = torch.cat(multi_crop_views[num_global_views:], dim=0)
-            feats.append(self.student_backbone(local_crops))
-        # one head call for all views: rows stay view-major (globals first), as in model.py:117-119
-        student_output = self.student_head(torch.cat(feats, dim=0))
+            crops.append(torch.cat(multi_crop_views[num_global_views:], dim=0))
+        # one backbone node and one head call for all views: rows stay view-major (globals first),
+        # as in model.py:117-119
+        student_output = self.student_head(self.student_backbone.forward_views(crops))
         with torch.no_grad():
             teacher_output = self._teacher_forward(global_crops)
         return teacher_output, student_output
@@ -101,8 +109,11 @@ class DINOViT(nn.Module):
         registration order (model.py:126-139) — a single multi-tensor kernel."""
         student = list(self.student_backbone.parameters()) + list(self.student_head.parameters())
         teacher = list(self.teacher_backbone.parameters()) + list(self.teacher_head.parameters())
-        ops.multi_ema([t.data for t in teacher], [s.detach().data for s in student], float(teacher_momentum))
-        torch.autograd.graph.increment_version(teacher)  # invalidate the bf16 weight shadows
+        shadows = [Fb.shadow_destination(t) for t in teacher]
+        ops.multi_ema_shadow([t.data for t in teacher], [s.detach().data for s in student], shadows,
+                             float(teacher_momentum))
+        torch.autograd.graph.increment_version(teacher)  # the kernel wrote through raw pointers ...
+        Fb.mark_shadows_fresh([t for t, sh in zip(teacher, shadows) if sh is not None])  # ... shadows included
 
     @torch.no_grad()
     @eager

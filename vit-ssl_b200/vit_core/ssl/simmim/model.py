@@ -13,6 +13,37 @@ from .masking import draw_mask
 from ..._backend import dp, eager
 
 
+class MaskedPrediction(torch.Tensor):
+    """The prediction tensor `SimMIMViT.forward` returns. It is an ordinary tensor in every respect
+    but one: `nn.L1Loss(reduction="mean")(pred, targets)` — the criterion the reference trainer
+    builds from configs/simmim/training.yaml:2-5 and calls at simmim_trainer.py:67 — dispatches to
+    the fused masked-L1 kernel (one pass forward, one pass backward with the GradScaler factor read
+    on the device) instead of torch's elementwise chain. Anything else strips the subclass."""
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func is torch.nn.functional.l1_loss:
+            out = _fused_l1(*args, **kwargs)
+            if out is not NotImplemented:
+                return out
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*args, **kwargs)
+
+
+def _fused_l1(input, target, size_average=None, reduce=None, reduction="mean", weight=None):
+    if (size_average is not None or reduce is not None or reduction != "mean" or weight is not None
+            or not (torch.is_tensor(input) and torch.is_tensor(target))
+            or input.shape != target.shape or not (input.is_cuda and target.is_cuda)
+            or input.dtype not in (torch.bfloat16, torch.float32)
+            or target.dtype not in (torch.bfloat16, torch.float32) or target.requires_grad):
+        return NotImplemented
+    with torch._C.DisableTorchFunctionSubclass():
+        pred = input.as_subclass(torch.Tensor)
+        tgt = target.as_subclass(torch.Tensor)
+        return Fb.l1_loss(pred, tgt)
+
+
 class SimMIMViT(nn.Module):
     def __init__(self, num_blocks: int, input_shape, embed_dim: int, patch_size: int, num_heads: int = 8,
                  mlp_dim: int = 3072, dropout: float = 0.1, mask_ratio: float = 0.6):
@@ -35,7 +66,7 @@ class SimMIMViT(nn.Module):
         p = self.patch_size
         N = (H // p) * (W // p)
         _, bool_mask, rows, inv = draw_mask(B, N, self.mask_ratio, x.device, want_indices=False)
-        x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+        x = Fb._as_image(x)  # fp32 (ToTensor output) or raw uint8 bytes, scaled by 1/255 in the kernels
         targets = ops.gather_patches_f32(x, rows, p)
         tokens = Fb.embed_patches(x, self, self.projection.weight, self.projection.bias, None,
                                   self.positional_embedding, p, mask_u8=bool_mask.view(torch.uint8).reshape(-1),
@@ -48,7 +79,7 @@ class SimMIMViT(nn.Module):
     def forward(self, x, return_bool_mask=False):
         dp.maybe_attach(self)  # data parallel under torchrun without touching the trainer
         masked, targets, bool_mask = self._encode_masked(x)
-        pred = Fb.autocast_out(Fb.mlp(masked, [self.simmim_head], [False]))
+        pred = Fb.autocast_out(Fb.mlp(masked, [self.simmim_head], [False])).as_subclass(MaskedPrediction)
         if return_bool_mask:
             return pred, targets, bool_mask.unsqueeze(-1)
         return pred, targets
