@@ -32,7 +32,11 @@ def _worker(rank, world, port, q):
                                     torch.nn.LayerNorm(8))
         frozen = model[0].bias
         frozen.requires_grad = False
+        v0 = model[2].weight._version
         sync = dp.attach(model, bucket_bytes=1024)  # tiny buckets -> several of them
+        # the broadcast writes through the parameter itself: version-keyed caches (bf16 weight shadows
+        # cast by a forward that ran before attach) see the change on every rank
+        assert model[2].weight._version > v0
         assert len(sync.buckets) > 1
         w0 = [p.detach().clone() for p in model.parameters()]
         gathered = [torch.zeros_like(w0[0]) for _ in range(world)]

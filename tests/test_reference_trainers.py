@@ -1,0 +1,167 @@
+"""Drop-in proof: the reference's OWN, unmodified `utils.model_builder.build_model`, `make_optimizer`,
+`make_criterion` and `SimMIMTrainer` / `DINOTrainer` / `SupervisedTrainer` (baseline/_ref, installed by
+baseline/install_reference.py) drive THIS repo's `vit_core` for one epoch on synthetic loaders —
+north_star: "train.py, the Hydra configs and the trainers in utils/trainers use it as a drop-in".
+Callers: utils/trainers/base_trainer.py:64-77, simmim_trainer.py:61-91, dino_trainer.py:82-112,
+supervised_trainer.py:30-48, utils/model_builder.py:104-184.
+
+Only three observability imports (ignite / torcheval / matplotlib, absent from this image) are
+stubbed (baseline/refenv.py); Hydra's DictConfig is stood in for by an attribute dict. Skipped when
+baseline/_ref is absent."""
+import os
+import sys
+
+import pytest
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from baseline import refenv  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refenv.available(), reason="baseline/_ref not installed")]
+
+
+def _config(kind, **model):
+    base = dict(
+        model=dict(in_channels=3, patch_size=8, embed_dim=128, num_blocks=2, num_heads=2, mlp_dim=256, dropout=0.1,
+                   num_classes=10, mask_ratio=0.6, output_dim=512, center_momentum=0.9),
+        data=dict(img_size=32),
+        training=dict(type=kind, num_epochs=1, warmup_epochs=1, warmup_initial_learning_rate=1e-6,
+                      warmup_final_learning_rate=1e-3, batch_size=8,
+                      optimizer=dict(name="AdamW", params=dict(lr=1e-6, weight_decay=1e-3)),
+                      lr_scheduler=dict(main=dict(name="CosineAnnealingLR", params=dict(eta_min=1e-6)),
+                                        warmup=dict(name="LinearWarmupScheduler", params={})),
+                      criterion=dict(name="L1Loss" if kind == "simmim" else "CrossEntropyLoss",
+                                     params=dict(reduction="mean")),
+                      student_temp=0.1, teacher_temp=0.04, teacher_temp_final=0.07, teacher_temp_scheduler="cosine",
+                      teacher_momentum_start=0.996, teacher_momentum_final=1.0, freeze_backbone=False),
+        eval=dict(interval=0, mode=None),
+        metrics=[],
+    )
+    base["model"].update(model)
+    return refenv.AttrDict.wrap(base)
+
+
+class _Images(Dataset):
+    def __init__(self, n, size, labels=False, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        self.x = torch.rand(n, 3, size, size, generator=g)
+        self.y = torch.randint(0, 10, (n,), generator=g) if labels else None
+
+    def __len__(self):
+        return len(self.x)
+
+    def __getitem__(self, i):
+        return (self.x[i], self.y[i]) if self.y is not None else self.x[i]
+
+
+class _MultiCrop(Dataset):
+    num_global_views = 2
+
+    def __init__(self, n, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        self.views = [torch.rand(n, 3, 32, 32, generator=g) for _ in range(2)] + [torch.rand(n, 3, 16, 16, generator=g) for _ in range(3)]
+
+    def __len__(self):
+        return self.views[0].shape[0]
+
+    def __getitem__(self, i):
+        return [v[i] for v in self.views]
+
+
+@pytest.fixture()
+def ref_callers(tmp_path, monkeypatch):
+    refenv.use_reference_callers_over_our_vit_core()
+    import vit_core
+    assert "vit-ssl_b200" in vit_core.__file__
+    import utils.trainers as trainers
+    assert trainers.__file__.startswith(refenv.REF)
+    from utils.model_builder import build_model
+    monkeypatch.setattr(os, "system", lambda *_a, **_k: 0)  # the rich logger shells out to `clear`
+    return trainers, build_model, str(tmp_path)
+
+
+def _params_snapshot(model):
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def test_simmim_trainer_fits_an_epoch_over_our_vit_core(ref_callers):
+    trainers, build_model, out = ref_callers
+    from vit_core.ssl.simmim.model import SimMIMViT
+    cfg = _config("simmim")
+    cfg["metrics"] = ["PSNR", "SSIM"]                # SimMIMTrainer._save_if_best reads both (simmim_trainer.py:140)
+    torch.manual_seed(3)
+    model = build_model(cfg).to("cuda")              # torch.compile wrapper, as train.py:113 does
+    assert isinstance(model._orig_mod, SimMIMViT)
+    before = _params_snapshot(model)
+    tr = trainers.SimMIMTrainer(model, out, cfg, DataLoader(_Images(16, 32), batch_size=8),
+                                DataLoader(_Images(8, 32, seed=1), batch_size=8), torch.device("cuda"))
+    assert type(tr.criterion).__name__ == "L1Loss" and type(tr.optimizer).__name__ == "AdamW"
+    tr.fit(1)
+    after = model.state_dict()
+    assert all(k.startswith("_orig_mod.") for k in after)
+    changed = [k for k in before if not torch.equal(before[k], after[k])]
+    assert len(changed) == len(before), set(before) - set(changed)        # every parameter trained
+    assert all(torch.isfinite(v).all() for v in after.values())
+    ck = torch.load(os.path.join(out, "last_model.pth"), weights_only=False)
+    assert set(ck["model_state_dict"]) == set(after) and ck["epoch"] == 1
+    assert os.path.exists(os.path.join(out, "best_model.pth"))
+
+
+def test_simmim_trainer_with_the_fused_optimizer_selected_by_config(ref_callers):
+    trainers, build_model, out = ref_callers
+    from vit_core.optim import FusedAdamW
+    cfg = _config("simmim")
+    cfg["metrics"] = ["PSNR", "SSIM"]
+    cfg["training"]["optimizer"]["name"] = "VitsslAdamW"                  # utils/train_utils.py:27 getattr(optim, name)
+    torch.manual_seed(3)
+    model = build_model(cfg).to("cuda")
+    before = _params_snapshot(model)
+    tr = trainers.SimMIMTrainer(model, out, cfg, DataLoader(_Images(16, 32), batch_size=8),
+                                DataLoader(_Images(8, 32, seed=1), batch_size=8), torch.device("cuda"))
+    assert isinstance(tr.optimizer, FusedAdamW)
+    tr.fit(1)
+    after = model.state_dict()
+    assert all(not torch.equal(before[k], after[k]) for k in before)
+    assert all(torch.isfinite(v).all() for v in after.values())
+    st = tr.optimizer.state_dict()["state"]
+    assert len(st) == len(before) and all(float(s["step"]) == 2.0 for s in st.values())  # 2 batches, no skipped step
+
+
+def test_dino_trainer_fits_an_epoch_over_our_vit_core(ref_callers):
+    trainers, build_model, out = ref_callers
+    from vit_core.ssl.dino.model import DINOViT
+    cfg = _config("dino")
+    cfg["metrics"] = ["CenterNorm", "TeacherSTD", "StudentSTD", "CosineSim"]   # dino_trainer.py:156 reads these
+    torch.manual_seed(5)
+    model = build_model(cfg).to("cuda")
+    assert isinstance(model._orig_mod, DINOViT)
+    before = _params_snapshot(model)
+    tr = trainers.DINOTrainer(model, out, cfg, DataLoader(_MultiCrop(12), batch_size=6),
+                              DataLoader(_MultiCrop(6, seed=1), batch_size=6), torch.device("cuda"))
+    tr.fit(1)
+    after = model.state_dict()
+    for k in before:
+        if k.endswith("center"):
+            assert not torch.equal(before[k], after[k]) and after[k].shape == (1, 512)
+        else:  # student trained by AdamW, teacher moved by the EMA (momentum 0.996 at epoch 1)
+            assert not torch.equal(before[k], after[k]), k
+        assert torch.isfinite(after[k]).all(), k
+    assert os.path.exists(os.path.join(out, "last_model.pth"))
+
+
+def test_supervised_trainer_fits_an_epoch_over_our_vit_core(ref_callers):
+    trainers, build_model, out = ref_callers
+    cfg = _config("supervised")
+    cfg["metrics"] = ["Accuracy"]
+    torch.manual_seed(7)
+    model = build_model(cfg).to("cuda")
+    before = _params_snapshot(model)
+    tr = trainers.SupervisedTrainer(model, out, cfg, DataLoader(_Images(16, 32, labels=True), batch_size=8),
+                                    DataLoader(_Images(8, 32, labels=True, seed=1), batch_size=8), torch.device("cuda"))
+    tr.fit(1)
+    after = model.state_dict()
+    assert all(not torch.equal(before[k], after[k]) for k in before)
+    assert all(torch.isfinite(v).all() for v in after.values())
+    assert os.path.exists(os.path.join(out, "best_model.pth"))

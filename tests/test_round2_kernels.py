@@ -1,0 +1,335 @@
+"""GPU tests of the round-2 additions: fused AdamW (+GradScaler hand-over, bf16 shadows), EMA with
+shadows, uint8 image kernels, bicubic positional-embedding kernel, multi-pass encoder-stack node,
+nn.L1Loss dispatch, the C-side launch profile, shape validation and DINO-loss generality."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vit_ref
+from parity_utils import rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------
+# fused AdamW vs torch.optim.AdamW (utils/train_utils.py:25-29; simmim_trainer.py:69-71)
+# ------------------------------------------------------------------------------------------
+def _param_sets(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(384, 384), (1536,), (7, 13), (3,), (1, 196, 384), (65, 33, 3), (2048, 384)]
+    return [torch.randn(*s, generator=g) for s in shapes]
+
+
+@pytest.mark.parametrize("wd,lr", [(1e-3, 1e-4), (0.0, 3e-3), (0.05, 1e-6)])
+def test_fused_adamw_matches_torch_adamw(wd, lr):
+    from vit_core.optim import FusedAdamW
+    init = _param_sets()
+    ours = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+    ref = [torch.nn.Parameter(t.clone().cuda().double()) for t in init]        # float64 torch AdamW as ground truth
+    ref32 = [torch.nn.Parameter(t.clone().cuda()) for t in init]               # float32 torch AdamW as yardstick
+    o1 = FusedAdamW(ours, lr=lr, weight_decay=wd)
+    o2 = torch.optim.AdamW(ref, lr=lr, weight_decay=wd)
+    o3 = torch.optim.AdamW(ref32, lr=lr, weight_decay=wd)
+    g = torch.Generator().manual_seed(1)
+    for step in range(4):
+        for a, b, c in zip(ours, ref, ref32):
+            gr = torch.randn(a.shape, generator=g).cuda() * (10.0 ** (step - 2))
+            a.grad, b.grad, c.grad = gr.clone(), gr.double(), gr.clone()
+        o1.step(); o2.step(); o3.step()
+        for a, b, c in zip(ours, ref, ref32):
+            e_ours = (a.detach().double() - b.detach()).abs().max().item()
+            e_t32 = (c.detach().double() - b.detach()).abs().max().item()
+            assert e_ours <= max(4 * e_t32, 1e-7 * b.detach().abs().max().item()), (step, a.shape, e_ours, e_t32)
+    for a, b in zip(ours, ref):
+        sa, sb = o1.state[a], o2.state[b]
+        assert float(sa["step"]) == float(sb["step"]) == 4.0
+        assert rel(sa["exp_avg"], sb["exp_avg"]) <= 1e-5 and rel(sa["exp_avg_sq"], sb["exp_avg_sq"]) <= 1e-5
+    sd = o1.state_dict()                                                       # base_trainer.py:99,112 checkpoints it
+    o4 = FusedAdamW([torch.nn.Parameter(t.clone().cuda()) for t in init], lr=lr, weight_decay=wd)
+    o4.load_state_dict(sd)
+    assert float(o4.state[o4.param_groups[0]["params"][0]]["step"]) == 4.0
+
+
+def test_fused_adamw_under_gradscaler_unscales_and_skips_on_inf():
+    from vit_core.optim import FusedAdamW
+    init = _param_sets(3)
+    ours = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+    ref = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+    o1, o2 = FusedAdamW(ours, lr=1e-3, weight_decay=1e-2), torch.optim.AdamW(ref, lr=1e-3, weight_decay=1e-2)
+    s1, s2 = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    g = torch.Generator().manual_seed(2)
+    for step in range(4):
+        for a, b in zip(ours, ref):
+            gr = torch.randn(a.shape, generator=g).cuda()
+            if step == 1:
+                gr.view(-1)[0] = float("inf")                                   # this step must be skipped by both
+            scale = float(s1.get_scale())
+            a.grad, b.grad = gr * scale, (gr * scale).clone()
+        for sc, opt in ((s1, o1), (s2, o2)):
+            sc.step(opt)
+            sc.update()
+        assert float(s1.get_scale()) == float(s2.get_scale())
+        for a, b in zip(ours, ref):
+            assert torch.isfinite(a).all()
+            assert (a.detach() - b.detach()).abs().max().item() <= 2e-6 * max(1.0, b.detach().abs().max().item()), (step, a.shape)
+    assert float(o1.state[ours[0]]["step"]) == 3.0                              # the inf step did not count
+    assert float(s1.get_scale()) == 512.0
+
+
+def test_fused_adamw_and_ema_keep_the_bf16_weight_shadows_fresh(monkeypatch):
+    """The optimizer / EMA kernels write the GEMM-operand shadows in their own pass: the next forward
+    must not launch a cast, and must see exactly bf16(updated fp32 weights)."""
+    from vit_core import EncoderBlock
+    from vit_core._backend import functional as Fb, ops
+    from vit_core.optim import FusedAdamW
+    torch.manual_seed(0)
+    blocks = torch.nn.ModuleList([EncoderBlock(128, 2, 256, 0.0) for _ in range(2)]).cuda().train()
+    opt = FusedAdamW(blocks.parameters(), lr=1e-2, weight_decay=1e-2)
+    x = torch.randn(3, 20, 128, device="cuda")
+    casts = []
+    real = ops.multi_cast_bf16
+    monkeypatch.setattr(ops, "multi_cast_bf16", lambda s, d: (casts.append(len(s)), real(s, d))[1])
+    out0, _ = Fb.encoder_stack(blocks, x)
+    assert casts == [12]                                                        # first use: 6 weight tensors per block
+    out0.square().mean().backward()
+    opt.step()
+    out1, _ = Fb.encoder_stack(blocks, x)
+    assert casts == [12], casts                                                 # no cast after the fused step
+    for blk in blocks:
+        a = blk.self_attention
+        sh = a.__dict__["_vitssl_cache"]["wqkv"][0]
+        want = torch.cat([a.w_query.weight, a.w_key.weight, a.w_value.weight]).detach().bfloat16()
+        assert torch.equal(sh, want)
+        assert torch.equal(blk.feed_forward.__dict__["_vitssl_cache"]["w2"][0], blk.feed_forward.linear_out.weight.detach().bfloat16())
+    assert not torch.equal(out0, out1)
+    for blk in blocks:                                                          # a plain torch update still invalidates
+        blk.self_attention.final_linear.weight.data.mul_(1.0)
+        with torch.no_grad():
+            blk.self_attention.final_linear.weight.mul_(0.5)
+    Fb.encoder_stack(blocks, x)
+    assert casts == [12, 2], casts
+
+
+def test_dino_ema_writes_teacher_shadows():
+    from oracle.cases import build_dino_case
+    from vit_core._backend import ops
+    from vit_core.ssl.dino import DINOViT
+    cfg, m, views, B = build_dino_case(DINOViT)
+    m.cuda().train()
+    m([v.cuda() for v in views], 2)
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.momentum_update_teacher(0.9)
+    blk = m.teacher_backbone.encoder_blocks[1]
+    want = (0.9 * before["teacher_backbone.encoder_blocks.1.feed_forward.linear_in.weight"]
+            + 0.1 * before["student_backbone.encoder_blocks.1.feed_forward.linear_in.weight"])
+    assert (blk.feed_forward.linear_in.weight - want).abs().max().item() <= 1e-6
+    assert torch.equal(blk.feed_forward.__dict__["_vitssl_cache"]["w1"][0], blk.feed_forward.linear_in.weight.detach().bfloat16())
+    calls = []
+    real = ops.multi_cast_bf16
+    ops.multi_cast_bf16 = lambda s, d: (calls.append(len(s)), real(s, d))[1]
+    try:
+        with torch.no_grad():
+            m.teacher_backbone(views[0].cuda())
+    finally:
+        ops.multi_cast_bf16 = real
+    assert calls == [], calls
+
+
+# ------------------------------------------------------------------------------------------
+# uint8 input: value = byte / 255 as torchvision's ToTensor computes it
+# ------------------------------------------------------------------------------------------
+def test_uint8_images_equal_totensor_floats():
+    from vit_core._backend import ops
+    from vit_core.ssl.simmim import SimMIMViT
+    g = torch.Generator().manual_seed(0)
+    xb = torch.randint(0, 256, (5, 3, 32, 48), dtype=torch.uint8, generator=g).cuda()
+    xf = xb.float().div(255)                                                    # ToTensor arithmetic
+    assert torch.equal(ops.im2col_bf16(xb, 8), ops.im2col_bf16(xf, 8))
+    assert torch.equal(ops.im2col_bf16(xb[:, :, :30, :45].contiguous(), 3), ops.im2col_bf16(xf[:, :, :30, :45].contiguous(), 3))
+    rows = torch.tensor([0, 7, 23, 5 * 24 - 1], dtype=torch.int32, device="cuda")
+    assert torch.equal(ops.gather_patches_f32(xb, rows, 8), ops.gather_patches_f32(xf, rows, 8))
+    torch.manual_seed(1)
+    m = SimMIMViT(num_blocks=2, input_shape=(3, 32, 32), embed_dim=128, patch_size=8, num_heads=2, mlp_dim=256,
+                  dropout=0.0, mask_ratio=0.6).cuda()
+    x8 = torch.randint(0, 256, (4, 3, 32, 32), dtype=torch.uint8, generator=g).cuda()
+    st = torch.cuda.get_rng_state()
+    p1, t1 = m(x8)
+    torch.cuda.set_rng_state(st)
+    p2, t2 = m(x8.float().div(255))
+    assert torch.equal(p1, p2) and torch.equal(t1, t2)
+
+
+# ------------------------------------------------------------------------------------------
+# bicubic positional-embedding resize (patch_embedding.py:26-48) vs F.interpolate, fwd + bwd
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("gin,gout,D", [((14, 14), (6, 6), 384), ((4, 4), (2, 2), 64), ((6, 6), (14, 14), 192), ((14, 14), (7, 5), 128)])
+def test_bicubic_pos_embedding_kernel_matches_f_interpolate(gin, gout, D):
+    from vit_core._backend import functional as Fb
+    torch.manual_seed(0)
+    pos = torch.rand(1, 1 + gin[0] * gin[1], D, device="cuda", requires_grad=True)
+    pos2 = pos.detach().clone().requires_grad_(True)
+    out = Fb.interpolate_pos_embedding(pos, gin, gout)
+    ref = vit_ref.interpolate_pos_encoding(pos2, gin, gout[0] * gout[1], gout[0], gout[1])
+    assert out.shape == ref.shape == (1, 1 + gout[0] * gout[1], D)
+    assert (out - ref).abs().max().item() <= 2e-6
+    dy = torch.randn_like(out)
+    (out * dy).sum().backward()
+    (ref * dy).sum().backward()
+    assert (pos.grad - pos2.grad).abs().max().item() <= 1e-5 * max(1.0, pos2.grad.abs().max().item())
+
+
+def test_dynamic_patch_embedding_local_crops_use_the_kernel_and_match():
+    from vit_core import DynamicPatchEmbedding
+    torch.manual_seed(0)
+    m = DynamicPatchEmbedding((3, 224, 224), 384, 16).cuda()
+    x = torch.rand(3, 3, 96, 96, device="cuda")
+    y = m(x)
+    w = {"pe." + k: v.detach().double().cpu() for k, v in m.state_dict().items()}
+    ref = vit_ref.dynamic_patch_embedding(w, "pe.", x.double().cpu(), 16, (14, 14))
+    assert y.shape == (3, 37, 384) and rel(y, ref) <= 1e-2
+    y.sum().backward()
+    assert m.positional_embedding.grad is not None and m.positional_embedding.grad.shape == (1, 197, 384)
+    # d(sum)/d(pos) = B * (column sums of the interpolation matrix), CLS row = B
+    assert abs(m.positional_embedding.grad[0, 0, 0].item() - 3.0) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# several token batches through the same blocks as ONE autograd node (DINO global + local passes)
+# ------------------------------------------------------------------------------------------
+def test_multi_pass_encoder_stack_matches_separate_nodes(monkeypatch):
+    from vit_core import EncoderBlock
+    from vit_core._backend import functional as Fb
+    torch.manual_seed(5)
+    blocks = torch.nn.ModuleList([EncoderBlock(128, 2, 256, 0.1) for _ in range(3)]).cuda().train()
+    xa, xb = torch.randn(4, 50, 128, device="cuda"), torch.randn(7, 17, 128, device="cuda")
+    seeds = iter([11, 22, 11, 22])
+    monkeypatch.setattr(Fb, "_new_seed", lambda: next(seeds))
+
+    def run(multi):
+        blocks.zero_grad(set_to_none=True)
+        a, b = xa.clone().requires_grad_(True), xb.clone().requires_grad_(True)
+        if multi:
+            oa, ob = Fb.encoder_stack_multi(blocks, [a, b])
+        else:
+            oa, ob = Fb.encoder_stack(blocks, a)[0], Fb.encoder_stack(blocks, b)[0]
+        (oa.square().mean() + ob.sum() * 1e-3).backward()
+        return oa.detach(), ob.detach(), [p.grad.clone() for p in blocks.parameters()], a.grad, b.grad
+
+    o1 = run(True)
+    o2 = run(False)
+    assert torch.equal(o1[0], o2[0]) and torch.equal(o1[1], o2[1])
+    for g1, g2 in zip(o1[2], o2[2]):
+        assert (g1 - g2).abs().max().item() <= 1e-5 * max(g2.abs().max().item(), 1e-6)
+    assert torch.allclose(o1[3], o2[3], atol=1e-6) and torch.allclose(o1[4], o2[4], atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# nn.L1Loss on the model's prediction runs the fused kernel (simmim_trainer.py:66-67)
+# ------------------------------------------------------------------------------------------
+def test_l1loss_on_model_output_dispatches_to_the_fused_kernel_and_matches_torch():
+    from vit_core.ssl.simmim import SimMIMViT
+    from vit_core.ssl.simmim.model import MaskedPrediction
+    torch.manual_seed(2)
+    m = SimMIMViT(num_blocks=2, input_shape=(3, 32, 32), embed_dim=128, patch_size=8, num_heads=2, mlp_dim=256,
+                  dropout=0.0, mask_ratio=0.6).cuda().train()
+    x = torch.rand(6, 3, 32, 32, device="cuda")
+    st = torch.cuda.get_rng_state()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred, tg = m(x)
+        assert isinstance(pred, MaskedPrediction) and pred.dtype == torch.bfloat16
+        loss = torch.nn.L1Loss()(pred, tg)
+    assert "_L1LossFn" in type(loss.grad_fn).__name__ and loss.dtype == torch.float32
+    scaler = torch.amp.GradScaler("cuda", init_scale=4096.0)
+    scaler.scale(loss).backward()
+    g1 = m.simmim_head.weight.grad.clone() / 4096.0
+    plain = pred.detach().as_subclass(torch.Tensor)
+    ref_loss = (plain.float() - tg).abs().mean()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * ref_loss.item()
+    # torch's own L1 on a plain tensor of the same forward: same gradients
+    m.zero_grad(set_to_none=True)
+    torch.cuda.set_rng_state(st)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred2, tg2 = m(x)
+        loss2 = F.l1_loss(pred2.as_subclass(torch.Tensor), tg2)
+    assert "_L1LossFn" not in type(loss2.grad_fn).__name__
+    loss2.backward()
+    assert rel_l2(g1, m.simmim_head.weight.grad) <= 1e-2
+    # everything else behaves like a plain tensor and drops the subclass
+    r = torch.clamp(pred.reshape(-1, 3, 8, 8), 0, 1)
+    assert type(r) is torch.Tensor and r.shape[1:] == (3, 8, 8)
+    assert type(torch.nn.L1Loss(reduction="sum")(pred, tg)) is torch.Tensor
+    assert abs(torch.nn.L1Loss(reduction="sum")(pred, tg).item() - (plain.float() - tg).abs().sum().item()) <= 1e-2 * ref_loss.item() * tg.numel()
+    assert type(torch.nn.MSELoss()(pred.float(), tg)) is torch.Tensor
+
+
+# ------------------------------------------------------------------------------------------
+# per-launch profile of the C-sequenced stack (what bench.py's roofline numbers are made of)
+# ------------------------------------------------------------------------------------------
+def test_c_side_profile_records_every_kernel_family_of_the_stack():
+    from vit_core import EncoderBlock
+    from vit_core._backend import functional as Fb, lib
+    torch.manual_seed(0)
+    L = 3
+    blocks = torch.nn.ModuleList([EncoderBlock(128, 2, 256, 0.1) for _ in range(L)]).cuda().train()
+    x = torch.randn(4, 64, 128, device="cuda", requires_grad=True)
+    Fb.encoder_stack(blocks, x)[0].sum().backward()                            # warm-up, not profiled
+    lib.profile_begin()
+    out, _ = Fb.encoder_stack(blocks, x)
+    out.sum().backward()
+    recs = lib.profile_collect()
+    kinds = [k for k, _, _ in recs]
+    assert kinds.count("attn_fwd") == L and kinds.count("attn_bwd") == L
+    assert kinds.count("add_layernorm") == (2 * L + 1) * 2
+    gemms = [k for k in kinds if k.startswith("gemm|")]
+    assert len(gemms) == 4 * L + 8 * L                                          # 4 forward + 4 dgrad + 4 wgrad per block
+    assert all(ms > 0 and work > 0 for _, ms, work in recs)
+    M = 4 * 64
+    assert f"gemm|{M}x256x128|a_mn=0 b_mn=0 epi=2" in kinds and f"gemm|{M}x256x128|a_mn=0 b_mn=1 epi=3" in kinds
+    assert [k for k, _, _ in lib.profile_collect()] == kinds                   # closed profile: reading again is harmless
+    Fb.encoder_stack(blocks, x)                                                 # and nothing is recorded when closed
+    lib.profile_begin()
+    assert lib.profile_collect() == []
+
+
+# ------------------------------------------------------------------------------------------
+# shape validation (advisor, round 1): a wrong-size positional embedding must raise, not read OOB
+# ------------------------------------------------------------------------------------------
+def test_patch_embedding_rejects_images_that_do_not_match_the_positional_embedding():
+    from vit_core import ConvolutionalPatchEmbedding, ManualPatchEmbedding
+    from vit_core.ssl.simmim import SimMIMViT
+    for cls in (ConvolutionalPatchEmbedding, ManualPatchEmbedding):
+        m = cls((3, 32, 32), 64, 8).cuda()
+        with pytest.raises(ValueError):
+            m(torch.rand(2, 3, 64, 64, device="cuda"))                          # larger grid than the embedding
+        with pytest.raises(ValueError):
+            m(torch.rand(2, 3, 16, 16, device="cuda"))                          # smaller grid
+        with pytest.raises(ValueError):
+            m(torch.rand(2, 1, 32, 32, device="cuda"))                          # wrong channel count
+    s = SimMIMViT(num_blocks=1, input_shape=(3, 32, 32), embed_dim=128, patch_size=8, num_heads=2, mlp_dim=256, dropout=0.0).cuda()
+    with pytest.raises(ValueError):
+        s(torch.rand(2, 3, 64, 64, device="cuda"))
+    with pytest.raises(ValueError):
+        s.inference_forward(torch.rand(2, 3, 16, 16, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------
+# DINO loss beyond the trainer's shapes (advisor, round 1): > 12 views, 3-4 teacher views, 2-D inputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tshape,sshape", [((2, 3, 1024), (14, 3, 1024)), ((3, 5, 512), (7, 5, 512)), ((4, 2, 256), (25, 2, 256)),
+                                           ((2, 2048), (6, 2048)), ((2, 2, 3, 256), (5, 2, 3, 256))])
+def test_dino_loss_general_shapes(tshape, sshape):
+    from vit_core.ssl.dino.loss import DINOLoss
+    g = torch.Generator().manual_seed(sum(tshape) + sum(sshape))
+    t = (torch.randn(*tshape, generator=g) * 2).bfloat16()
+    s0 = (torch.randn(*sshape, generator=g) * 1.5).bfloat16()
+    c = torch.randn(1, tshape[-1], generator=g) * 0.1
+    s = s0.cuda().requires_grad_(True)
+    loss = DINOLoss(0.05, 0.1)(t.cuda(), s, c.cuda())
+    sb = s0.double().requires_grad_(True)
+    ref = vit_ref.dino_loss(t.double(), sb, c.double(), 0.05, 0.1)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-4 * abs(ref.item()), (loss.item(), ref.item())
+    loss.backward()
+    assert rel_l2(s.grad, sb.grad) <= 1e-2
+    with pytest.raises(ValueError):
+        DINOLoss(0.05, 0.1)(t.cuda()[..., :8], s, c.cuda())

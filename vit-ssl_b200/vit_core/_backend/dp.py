@@ -24,6 +24,22 @@ from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
 from torch.autograd import Variable
 
 DEFAULT_BUCKET_BYTES = 32 << 20
+# bench.py sets this to a list to measure EXPOSED communication: (event, event) pairs recorded on the
+# compute stream around every wait for the all-reduce stream (the span the compute stream is stalled)
+WAIT_TRACE = None
+
+
+def _wait_for(comm_stream) -> None:
+    cur = torch.cuda.current_stream()
+    if WAIT_TRACE is None:
+        cur.wait_stream(comm_stream)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    cur.wait_stream(comm_stream)
+    e1.record(cur)
+    WAIT_TRACE.append((e0, e1))
+
 _SYNCS: "weakref.WeakSet" = weakref.WeakSet()  # live GradSync objects (sync_for looks a parameter up here)
 
 
@@ -45,15 +61,18 @@ def broadcast_module_(module: torch.nn.Module, src: int = 0) -> None:
     """Make every rank start from rank `src`'s parameters and buffers."""
     if not is_distributed():
         return
-    tensors = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
+    tensors = list(module.parameters()) + list(module.buffers())
     by_dtype = {}
     for t in tensors:
         by_dtype.setdefault((t.dtype, t.device), []).append(t)
-    for group in by_dtype.values():
-        flat = _flatten_dense_tensors(group)
-        dist.broadcast(flat, src=src)
-        for t, f in zip(group, _unflatten_dense_tensors(flat, group)):
-            t.copy_(f)
+    with torch.no_grad():
+        for group in by_dtype.values():
+            flat = _flatten_dense_tensors([t.detach() for t in group])
+            dist.broadcast(flat, src=src)
+            for t, f in zip(group, _unflatten_dense_tensors(flat, group)):
+                # an in-place copy on the tensor itself (not `.data`) bumps its version counter, which
+                # is what invalidates bf16 weight shadows cast by an earlier forward on this rank
+                t.copy_(f)
 
 
 class GradSync:
@@ -144,7 +163,7 @@ class GradSync:
         """Make the current stream wait for the reductions issued so far (the autograd engine is
         about to read / accumulate the tensors `prereduce` is averaging in place)."""
         if self.comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            _wait_for(self.comm_stream)
 
     def _launch(self, bi: int) -> None:
         grads = [p.grad for p in self.buckets[bi] if p.grad is not None and id(p) not in self.prereduced]
@@ -184,7 +203,7 @@ class GradSync:
             if not self.launched[bi] and self.ready[bi] > 0:
                 self._launch(bi)
         if self.comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            _wait_for(self.comm_stream)
         self.ready = [0] * len(self.buckets)
         self.launched = [False] * len(self.buckets)
         self.callback_queued = False
