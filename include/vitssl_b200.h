@@ -60,11 +60,18 @@ int vitssl_profile_read(int64_t index, char* kind_out, int64_t kind_cap, double*
  *           feed_forward.py:26-27) | DGELU (C <- acc * mask/(1-p) * gelu'(aux)).
  * out_fp32: C is fp32, else bf16. split_k: 0 = off, -1 = auto, n = n splits (fp32 NONE only;
  * C is zeroed on `stream` and the partial sums are accumulated with TMA reduce-add), -2 = auto
- * with C already zeroed by the caller (one memset can then serve many GEMMs). */
+ * and ACCUMULATE into C, which the caller initialised (one memset can then serve many GEMMs, and
+ * several calls — e.g. two passes over the same layer — can add into one gradient buffer). */
 #define VITSSL_EPI_NONE 0
 #define VITSSL_EPI_BIAS 1
 #define VITSSL_EPI_BIAS_GELU 2
 #define VITSSL_EPI_DGELU 3
+/* The pair the encoder stack uses (feed_forward.py:26-27 and its backward): the forward GEMM saves the
+ * whole backward factor instead of the pre-activation, so the backward epilogue is one multiply —
+ *   BIAS_GELU_D: u = bf16(acc+bias); C <- dropout(gelu(u)); aux <- mask/(1-p) * gelu'(u)   (bf16)
+ *   MUL:         C <- alpha * acc * aux                                                    (bf16) */
+#define VITSSL_EPI_BIAS_GELU_D 4
+#define VITSSL_EPI_MUL 5
 int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,
                      int64_t lda, int64_t ldb, int64_t ldc, int a_mn, int b_mn, int epilogue,
                      const float* bias, void* aux, int64_t ld_aux, float alpha, int out_fp32,
@@ -160,7 +167,7 @@ typedef struct {
   float* const* xs; float* const* mean1; float* const* rstd1; void* const* xn1;
   void* const* qkv; void* const* ctx; float* const* lse;
   float* const* xmid; float* const* mean2; float* const* rstd2; void* const* xn2;
-  void* const* u; void* const* h;
+  void* const* u; void* const* h;  /* u: saved GELU backward factor mask/(1-p) * gelu'(pre-activation) */
 } vitssl_encoder_fwd_args;
 int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* args, vitssl_stream_t stream);
 

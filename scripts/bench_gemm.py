@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "vit-ssl_b200"))
 import torch
 from vit_core._backend import ops
-from vit_core._backend.ops import EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_NONE
+from vit_core._backend.ops import EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_D, EPI_DGELU, EPI_MUL, EPI_NONE
 
 M = int(os.environ.get("M", 50176))
 REPS = int(os.environ.get("REPS", 20))
@@ -41,6 +41,8 @@ w1, w2, wqkv, wo = rnd(F, D), rnd(D, F), rnd(3 * D, D), rnd(D, D)
 b1, b2 = torch.randn(F, device=dev), torch.randn(D, device=dev)
 
 add("ffn1 fwd gelu  MxFxD", lambda i: ops.gemm(xs[i], w1, epilogue=EPI_BIAS_GELU, bias=b1, aux=us[i], dropout_p=P, seed=1, offset=1), 2.0 * M * F * D)
+add("ffn1 fwd gelu_d MxFxD", lambda i: ops.gemm(xs[i], w1, epilogue=EPI_BIAS_GELU_D, bias=b1, aux=us[i], dropout_p=P, seed=1, offset=1), 2.0 * M * F * D)
+add("ffn2 dgrad mul MxFxD", lambda i: ops.gemm(xs[i], w2, b_mn=True, epilogue=EPI_MUL, aux=hs[i]), 2.0 * M * F * D)
 add("ffn1 fwd gelu p=0", lambda i: ops.gemm(xs[i], w1, epilogue=EPI_BIAS_GELU, bias=b1, aux=us[i]), 2.0 * M * F * D)
 add("ffn1 fwd bias  MxFxD", lambda i: ops.gemm(xs[i], w1, epilogue=EPI_BIAS, bias=b1), 2.0 * M * F * D)
 add("ffn1 fwd none  MxFxD", lambda i: ops.gemm(xs[i], w1), 2.0 * M * F * D)

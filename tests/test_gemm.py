@@ -123,6 +123,44 @@ def test_gemm_dropout_epilogue_is_consistent():
     assert torch.equal((dud == 0) & nz2 & nz, dropped & nz2)
 
 
+@pytest.mark.parametrize("M,N,K", [(777, 1536, 384), (4116, 3072, 768), (50, 64, 64)])
+def test_gemm_gelu_with_saved_backward_factor_and_mul_epilogue(M, N, K):
+    """BIAS_GELU_D saves mask/(1-p) * gelu'(u) instead of u; MUL multiplies the dgrad accumulator by it
+    (the pair the encoder stack uses): same h as BIAS_GELU, and du equals the DGELU result to bf16
+    rounding of the saved factor; with dropout both see the SAME mask without regenerating it."""
+    ops = _ops()
+    a, w = _mk((M, K), 21), _mk((N, K), 22)
+    bias = torch.randn(N, device="cuda") * 0.1
+    u = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    gf = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    h_old = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, aux=u)
+    h_new = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU_D, bias=bias, aux=gf)
+    assert torch.equal(h_old, h_new)
+    ud = u.double()
+    gp = 0.5 * (1 + torch.erf(ud / math.sqrt(2))) + ud * torch.exp(-0.5 * ud * ud) / math.sqrt(2 * math.pi)
+    assert (gf.double() - gp).abs().max().item() <= 6e-3          # bf16 rounding of a value in [-0.13, 1.13]
+    dy, w2 = _mk((M, K), 23), _mk((K, N), 24)
+    du = ops.gemm(dy, w2, b_mn=True, epilogue=ops.EPI_MUL, aux=gf)
+    du_ref = (dy.double() @ w2.double()) * gp
+    assert _err(du, du_ref) < 8e-3
+    assert _err(du, (dy.double() @ w2.double()) * gf.double()) < 5e-3   # exactly acc * saved factor, rounded once
+    du_old = ops.gemm(dy, w2, b_mn=True, epilogue=ops.EPI_DGELU, aux=u)
+    assert ((du.double() - du_old.double()).norm() / du_old.double().norm()).item() < 4e-3
+    if N % 8 == 0:
+        p = 0.25
+        hd_old = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, aux=u, dropout_p=p, seed=77, offset=5)
+        hd = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU_D, bias=bias, aux=gf, dropout_p=p, seed=77, offset=5)
+        assert torch.equal(hd, hd_old)
+        nz = (h_new != 0) & (gp.abs() > 1e-3)
+        dropped = (hd == 0) & nz
+        assert torch.equal((gf == 0) & nz, dropped)                    # the saved factor carries the same mask
+        kept = (~dropped) & nz & (gp.abs() > 5e-2)
+        assert ((gf.double()[kept] / gp[kept]) - 1 / (1 - p)).abs().max().item() < 0.02
+        dud = ops.gemm(dy, w2, b_mn=True, epilogue=ops.EPI_MUL, aux=gf)
+        dud_old = ops.gemm(dy, w2, b_mn=True, epilogue=ops.EPI_DGELU, aux=u, dropout_p=p, seed=77, offset=5)
+        assert ((dud.double() - dud_old.double()).norm() / dud_old.double().norm()).item() < 4e-3
+
+
 def test_gemm_unaligned_falls_back_to_simt():
     ops = _ops()
     # 10-class head: wgrad has a [B,10] operand whose pitch is not 16-byte aligned

@@ -74,9 +74,9 @@ extern "C" int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* a, cudaSt
     VITSSL_TIMED("add_layernorm", (double)M * D * 12,
                  vitssl_add_layernorm_fwd(x_l, D, a->y1, a->xmid[l], a->g2[l], a->be2[l], a->xn2[l], a->mean2[l],
                                           a->rstd2[l], M, D, a->eps, p, a->seed, (uint64_t)(3 * l), stream));
-    // FFN: u = xn2 W1^T + b1 (saved), h = drop(gelu(u)); y2 = h W2^T + b2   feed_forward.py:26-28
-    VITSSL_TIMED(gemm_kind(M, F, D, 0, 0, 2).s, gemm_flops(M, F, D),
-                 vitssl_gemm_bf16(a->xn2[l], a->w1[l], a->h[l], M, F, D, D, D, F, 0, 0, VITSSL_EPI_BIAS_GELU, a->b1[l],
+    // FFN: u = xn2 W1^T + b1, h = drop(gelu(u)), saved: h and mask/(1-p) gelu'(u); y2 = h W2^T + b2   feed_forward.py:26-28
+    VITSSL_TIMED(gemm_kind(M, F, D, 0, 0, VITSSL_EPI_BIAS_GELU_D).s, gemm_flops(M, F, D),
+                 vitssl_gemm_bf16(a->xn2[l], a->w1[l], a->h[l], M, F, D, D, D, F, 0, 0, VITSSL_EPI_BIAS_GELU_D, a->b1[l],
                                   a->u[l], F, 1.0f, 0, 0, p, a->seed, (uint64_t)(3 * l + 1), stream));
     void* y2 = a->y2[l & 1];
     VITSSL_TIMED(gemm_kind(M, D, F, 0, 0, 1).s, gemm_flops(M, D, F),
@@ -115,9 +115,9 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
   for (int64_t l = l_hi - 1; l >= l_lo; --l) {
     const void* dy2 = a->dbranch;
     // FFN backward
-    VITSSL_TIMED(gemm_kind(M, F, D, 0, 1, 3).s, gemm_flops(M, F, D),
-                 vitssl_gemm_bf16(dy2, f->w2[l], a->du, M, F, D, D, F, F, 0, 1, VITSSL_EPI_DGELU, nullptr, f->u[l], F,
-                                  1.0f, 0, 0, p, f->seed, (uint64_t)(3 * l + 1), stream));
+    VITSSL_TIMED(gemm_kind(M, F, D, 0, 1, VITSSL_EPI_MUL).s, gemm_flops(M, F, D),
+                 vitssl_gemm_bf16(dy2, f->w2[l], a->du, M, F, D, D, F, F, 0, 1, VITSSL_EPI_MUL, nullptr, f->u[l], F,
+                                  1.0f, 0, 0, 0.f, 0, 0, stream));
     // dW2 = dy2^T h with db2 = colsum(dy2) from the same kernel (ones-operand MMA); shapes the fused
     // form does not cover (CTA pairs) fall back to GEMM + column-sum pass
     {

@@ -160,6 +160,16 @@ __device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint
         c[i >> 1] = pack_bf16(x0, x1);
       }
     }
+  } else if constexpr (MODE == VITSSL_EPI_MUL) {
+    // C = alpha * acc * aux: backward of GELU(+dropout) with the factor mask/(1-p) * gelu'(u) saved by
+    // the forward (BIAS_GELU_D) — no polynomial, no Philox, no exp in the backward epilogue
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const uint32_t up = u[i >> 1];
+      float d0, d1;
+      upk2(fmul2(fmul2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), al), pk2(bf16_lo(up), bf16_hi(up))), d0, d1);
+      c[i >> 1] = pack_bf16(d0, d1);
+    }
   } else {
     const bool drop = e.drop_th2 != 0;
     const float sc = drop ? e.drop_scale : 1.0f;
@@ -177,7 +187,7 @@ __device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint
         keep[3] = dropout_lane_mask2(r.w, e.drop_th2);
       }
       float b[8];
-      if constexpr (MODE == VITSSL_EPI_BIAS_GELU) load_bias8(e.bias, nb, g, ncols, b);
+      if constexpr (MODE == VITSSL_EPI_BIAS_GELU || MODE == VITSSL_EPI_BIAS_GELU_D) load_bias8(e.bias, nb, g, ncols, b);
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
         const int i = 8 * g + j;
@@ -190,6 +200,25 @@ __device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint
           float h0, h1;
           upk2(fmul2(fmul2(pk2(u0, u1), scv), normal_cdf2_sat(u0, u1)), h0, h1);
           c[i >> 1] = pack_bf16(h0, h1) & keep[j >> 1];
+        } else if constexpr (MODE == VITSSL_EPI_BIAS_GELU_D) {
+          // h = dropout(u Phi(u)) as above; the aux output is the whole backward factor
+          // mask/(1-p) * (Phi(u) + u phi(u)) instead of u: the exp rides on the idle MUFU pipe here
+          // and the backward GEMM's epilogue shrinks to one multiply (VITSSL_EPI_MUL)
+          float x0, x1;
+          upk2(ffma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), al, pk2(b[j], b[j + 1])), x0, x1);
+          const uint32_t up = pack_bf16(x0, x1);
+          const float u0 = bf16_lo(up), u1 = bf16_hi(up);
+          const f32x2 uu = pk2(u0, u1);
+          const f32x2 cdf = normal_cdf2_sat(u0, u1);
+          float a0, a1;
+          upk2(fmul2(fmul2(uu, uu), pk2(-0.72134752044448170f, -0.72134752044448170f)), a0, a1);
+          const f32x2 pdf = pk2(ex2_approx(a0), ex2_approx(a1));
+          const f32x2 gp = ffma2(fmul2(uu, pk2(0.3989422804014327f, 0.3989422804014327f)), pdf, cdf);  // Phi + u phi
+          float h0, h1, g0, g1;
+          upk2(fmul2(fmul2(uu, scv), cdf), h0, h1);
+          upk2(fmul2(gp, scv), g0, g1);
+          c[i >> 1] = pack_bf16(h0, h1) & keep[j >> 1];
+          u[i >> 1] = pack_bf16(g0, g1) & keep[j >> 1];
         } else {
           const uint32_t up = u[i >> 1];
           const float u0 = bf16_lo(up), u1 = bf16_hi(up);
@@ -268,8 +297,9 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
                                                 const GemmShape& s, const GemmEpi& e, uint8_t* stg,
                                                 uint64_t* tfull_bar, const TileCtx& tc,
                                                 uint32_t tmem_base, int q, int cg, int lane) {
-  static_assert(!(OUT_F32 && (MODE == VITSSL_EPI_BIAS_GELU || MODE == VITSSL_EPI_DGELU)),
-                "GELU epilogues write bf16");
+  static_assert(!(OUT_F32 && MODE >= VITSSL_EPI_BIAS_GELU), "GELU / MUL epilogues write bf16");
+  constexpr bool kAuxIn = MODE == VITSSL_EPI_DGELU || MODE == VITSSL_EPI_MUL;             // aux is read
+  constexpr bool kAuxOut = MODE == VITSSL_EPI_BIAS_GELU || MODE == VITSSL_EPI_BIAS_GELU_D;  // aux is written
   constexpr int NC = BN / 32;
   const int num_work = s.m_tiles * s.n_tiles * s.splits;
   int acc = 0;
@@ -283,7 +313,7 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
     const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
     uint32_t up[16];
-    if constexpr (MODE == VITSSL_EPI_DGELU) {  // first chunk's pre-activations: in flight while the MMAs finish
+    if constexpr (kAuxIn) {  // first chunk's saved operand: in flight while the MMAs finish
       if (cg < nch) load_aux_row(e.aux, e.ld_aux, row0 + lane, s.M, nbase + cg * 32, min(32, s.N - nbase - cg * 32), up);
     }
     mbar_wait(&tfull_bar[acc], acc_phase);
@@ -310,7 +340,7 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
       uint32_t r[32];
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the single-lane sections
       tmem_ld_32x32(tcol + c * 32, r);
-      if constexpr (MODE == VITSSL_EPI_DGELU) {
+      if constexpr (kAuxIn) {
         if (c != cg) load_aux_row(e.aux, e.ld_aux, row0 + lane, s.M, nb, ncols, up);
       }
       tmem_ld_wait();
@@ -330,14 +360,14 @@ __device__ __forceinline__ void epilogue_staged(const CUtensorMap* tmap_c, const
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         stage_row_bf16(stg, lane, cp);
-        if constexpr (MODE == VITSSL_EPI_BIAS_GELU) stage_row_bf16(stg + 2048, lane, up);
+        if constexpr (kAuxOut) stage_row_bf16(stg + 2048, lane, up);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
         if (OUT_F32 && e.atomic) tma_reduce_add_2d(tmap_c, stg, nb, row0);  // split-K partial sum
         else tma_store_2d(tmap_c, stg, nb, row0);
-        if constexpr (MODE == VITSSL_EPI_BIAS_GELU) tma_store_2d(tmap_aux, stg + 2048, nb, row0);
+        if constexpr (kAuxOut) tma_store_2d(tmap_aux, stg + 2048, nb, row0);
         tma_store_commit();
       }
     }
@@ -472,7 +502,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tma_prefetch_desc(&tmap_b);
     if (e.tma_out) {
       tma_prefetch_desc(&tmap_c);
-      if (e.mode == VITSSL_EPI_BIAS_GELU || e.mode == VITSSL_EPI_DGELU) tma_prefetch_desc(&tmap_aux);
+      if (e.mode >= VITSSL_EPI_BIAS_GELU) tma_prefetch_desc(&tmap_aux);
     }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -637,6 +667,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     } else if (e.mode == VITSSL_EPI_DGELU) {
       epilogue_staged<BN, VITSSL_EPI_DGELU, false>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q, cg,
                                                    lane);
+    } else if (e.mode == VITSSL_EPI_BIAS_GELU_D) {
+      epilogue_staged<BN, VITSSL_EPI_BIAS_GELU_D, false>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q,
+                                                         cg, lane);
+    } else if (e.mode == VITSSL_EPI_MUL) {
+      epilogue_staged<BN, VITSSL_EPI_MUL, false>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q, cg,
+                                                 lane);
     } else if (e.mode == VITSSL_EPI_BIAS) {
       if (e.out_fp32)
         epilogue_staged<BN, VITSSL_EPI_BIAS, true>(&tmap_c, &tmap_aux, s, e, stg, tfull_bar, tc, tmem_base, q, cg,
@@ -716,13 +752,19 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A,
     const int m = m0 + ty + 8 * j;
     if (m >= M) continue;
     float v = acc[j] * e.alpha;
-    if (e.mode == VITSSL_EPI_BIAS || e.mode == VITSSL_EPI_BIAS_GELU) v += e.bias[n];
+    if (e.mode == VITSSL_EPI_BIAS || e.mode == VITSSL_EPI_BIAS_GELU || e.mode == VITSSL_EPI_BIAS_GELU_D) v += e.bias[n];
     if (e.mode == VITSSL_EPI_BIAS_GELU) {
       v = bf16_round(v);
       e.aux[static_cast<long long>(m) * e.ld_aux + n] = __float2bfloat16_rn(v);
       v = gelu_erf(v);
+    } else if (e.mode == VITSSL_EPI_BIAS_GELU_D) {  // (no dropout on this path)
+      v = bf16_round(v);
+      e.aux[static_cast<long long>(m) * e.ld_aux + n] = __float2bfloat16_rn(gelu_erf_grad(v));
+      v = gelu_erf(v);
     } else if (e.mode == VITSSL_EPI_DGELU) {
       v *= gelu_erf_grad(__bfloat162float(e.aux[static_cast<long long>(m) * e.ld_aux + n]));
+    } else if (e.mode == VITSSL_EPI_MUL) {
+      v *= __bfloat162float(e.aux[static_cast<long long>(m) * e.ld_aux + n]);
     }
     if (e.out_fp32)
       reinterpret_cast<float*>(e.c)[static_cast<long long>(m) * e.ldc + n] = v;
@@ -826,11 +868,11 @@ static int gemm_impl(const void* A, const void* B, void* C, int64_t M, int64_t N
                  (long long)M, (long long)N, (long long)K);
   VITSSL_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), VITSSL_ERR_SHAPE,
                  "gemm: dimension exceeds int32");
-  VITSSL_REQUIRE(epilogue >= VITSSL_EPI_NONE && epilogue <= VITSSL_EPI_DGELU, VITSSL_ERR_ARG,
+  VITSSL_REQUIRE(epilogue >= VITSSL_EPI_NONE && epilogue <= VITSSL_EPI_MUL, VITSSL_ERR_ARG,
                  "gemm: bad epilogue %d", epilogue);
-  if (epilogue == VITSSL_EPI_BIAS || epilogue == VITSSL_EPI_BIAS_GELU)
+  if (epilogue == VITSSL_EPI_BIAS || epilogue == VITSSL_EPI_BIAS_GELU || epilogue == VITSSL_EPI_BIAS_GELU_D)
     VITSSL_REQUIRE(bias != nullptr, VITSSL_ERR_ARG, "gemm: epilogue needs bias");
-  if (epilogue == VITSSL_EPI_BIAS_GELU || epilogue == VITSSL_EPI_DGELU)
+  if (epilogue >= VITSSL_EPI_BIAS_GELU)
     VITSSL_REQUIRE(aux != nullptr && ld_aux >= N, VITSSL_ERR_ARG, "gemm: epilogue needs aux");
   VITSSL_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, VITSSL_ERR_ARG, "gemm: dropout_p out of range");
   if (dropout_p > 0.f)
@@ -849,7 +891,7 @@ static int gemm_impl(const void* A, const void* B, void* C, int64_t M, int64_t N
                       (reinterpret_cast<uintptr_t>(B) % 16 == 0) && (lda % 8 == 0) &&
                       (ldb % 8 == 0);
   const int elt = out_fp32 ? 4 : 2;
-  const bool gelu_mode = epilogue == VITSSL_EPI_BIAS_GELU || epilogue == VITSSL_EPI_DGELU;
+  const bool gelu_mode = epilogue >= VITSSL_EPI_BIAS_GELU;  // every epilogue with an aux operand (bf16 in/out)
   bool out_ok = (reinterpret_cast<uintptr_t>(C) % 16 == 0) && ((ldc * elt) % 16 == 0);
   if (gelu_mode)
     out_ok = out_ok && !out_fp32 && (reinterpret_cast<uintptr_t>(aux) % 16 == 0) && (ld_aux % 8 == 0);
@@ -909,7 +951,10 @@ static int gemm_impl(const void* A, const void* B, void* C, int64_t M, int64_t N
   }
   s.kblocks_per_split = (s.kblocks_total + splits - 1) / splits;
   s.splits = (s.kblocks_total + s.kblocks_per_split - 1) / s.kblocks_per_split;
-  e.atomic = s.splits > 1 ? 1 : 0;
+  // split_k == -2 means "accumulate into C": with a single split the partial sum is still ADDED (TMA
+  // reduce-add), so several calls can contribute to one gradient buffer (two passes over the same
+  // encoder blocks accumulate their weight gradients into one zeroed buffer)
+  e.atomic = (s.splits > 1 || (split_k == -2 && out_fp32 && epilogue == VITSSL_EPI_NONE)) ? 1 : 0;
   e.vec_ok = out_ok ? 1 : 0;
   e.tma_out = out_ok ? 1 : 0;  // split-K partials go through the same staging tiles as a TMA reduce-add
   if (e.atomic && split_k != -2) {  // -2: the caller hands over a zeroed C (one memset for many GEMMs)

@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import dp, ops
-from .ops import EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_NONE
+from .ops import EPI_BIAS, EPI_BIAS_GELU_D, EPI_MUL, EPI_NONE
 
 
 # ----------------------------------------------------------------------------------------
@@ -225,8 +225,8 @@ class _EncoderStackFn(torch.autograd.Function):
             xmid, xn2, mean2, rstd2 = ops.add_layernorm_fwd(xs, y1, g2, be2, dropout_p=p, seed=seed,
                                                             offset=3 * l)
             u = torch.empty((M, F_), device=x.device, dtype=torch.bfloat16)
-            h = ops.gemm(xn2, w1, epilogue=EPI_BIAS_GELU, bias=b1, aux=u, dropout_p=p, seed=seed,
-                         offset=3 * l + 1)
+            h = ops.gemm(xn2, w1, epilogue=EPI_BIAS_GELU_D, bias=b1, aux=u, dropout_p=p, seed=seed,
+                         offset=3 * l + 1)  # u <- mask/(1-p) * gelu'(pre-activation): the whole backward factor
             y2 = ops.gemm(h, w2, epilogue=EPI_BIAS, bias=b2)
             stream, branch = xmid, y2
             last_qkv = qkv3
@@ -289,8 +289,7 @@ class _EncoderStackFn(torch.autograd.Function):
             xs, mean1, rstd1, xn1, qkv3, ctx_, lse, xmid, mean2, rstd2, xn2, u, h = saved[l]
             saved[l] = None
             dy2 = dbranch
-            du = ops.gemm(dy2, w2, b_mn=True, epilogue=EPI_DGELU, aux=u, dropout_p=p, seed=seed,
-                          offset=3 * l + 1)
+            du = ops.gemm(dy2, w2, b_mn=True, epilogue=EPI_MUL, aux=u)
             dW2 = ops.gemm(dy2, h, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
             db2 = ops.colsum_bf16(dy2)
             dxn2 = ops.gemm(du, w1, b_mn=True)
@@ -466,7 +465,7 @@ class _MLPFn(torch.autograd.Function):
             out_dtype = meta.out_dtype if last else torch.bfloat16
             if meta.gelu[i]:
                 u = torch.empty((cur.shape[0], w.shape[0]), device=cur.device, dtype=torch.bfloat16)
-                cur = ops.gemm(cur, w, epilogue=EPI_BIAS_GELU, bias=b, aux=u, dropout_p=p, seed=seed, offset=i)
+                cur = ops.gemm(cur, w, epilogue=EPI_BIAS_GELU_D, bias=b, aux=u, dropout_p=p, seed=seed, offset=i)
                 pre.append(u)
             else:
                 cur = ops.gemm(cur, w, epilogue=EPI_BIAS if b is not None else EPI_NONE, bias=b,
@@ -496,8 +495,7 @@ class _MLPFn(torch.autograd.Function):
                 grads[2 * i + 1] = ops.colsum_bf16(dy)
             if i > 0:
                 if meta.gelu[i - 1]:
-                    dy = ops.gemm(dy, w, b_mn=True, epilogue=EPI_DGELU, aux=pre[i - 1], dropout_p=p,
-                                  seed=seed, offset=i - 1)
+                    dy = ops.gemm(dy, w, b_mn=True, epilogue=EPI_MUL, aux=pre[i - 1])
                 else:
                     dy = ops.gemm(dy, w, b_mn=True)
             elif ctx.needs_input_grad[0]:

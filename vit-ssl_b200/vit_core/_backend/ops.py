@@ -9,7 +9,7 @@ import torch
 
 from . import lib as _l
 
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU = 0, 1, 2, 3
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_BIAS_GELU_D, EPI_MUL = 0, 1, 2, 3, 4, 5
 
 # Optional per-launch timing used by bench.py's instrumented pass: when PROFILE is a list, the
 # wrapped kernels are bracketed by CUDA events on the launching stream and
