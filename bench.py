@@ -428,6 +428,14 @@ def run_gpu_arm(args):
     value = world * B * args.steps / (ms_total / 1e3)
     final_loss = float(loss.detach())
 
+    # host time to ISSUE a step (no synchronisation inside): the margin by which the step is GPU-bound
+    barrier()
+    th0 = time.perf_counter()
+    for i in range(5):
+        step(dev_in[i % n_host])
+    host_issue_ms = (time.perf_counter() - th0) / 5 * 1e3
+    barrier()
+
     # ---- timed region 2: end to end (pinned host -> device each step, loss read back each step) ----
     copy_stream = torch.cuda.Stream()
 
@@ -587,7 +595,8 @@ def run_gpu_arm(args):
                     "ms_per_step": round(e2e_ms, 3), "input": "fp32 images from pinned host memory (ToTensor output, what the reference's loaders yield)"},
             "e2e_u8": {"value": round(e2e8_value, 1), "unit": "images/s", "h2d_bytes_per_step": in_bytes // 4, "d2h_bytes_per_step": 4,
                        "ms_per_step": round(e2e8_ms, 3), "input": "raw uint8 images from pinned host memory, /255 inside the patch kernels (SURVEY 8(f)3)"},
-            "gpu_launches": int(launches), "loss": round(final_loss, 5), "clocks": clocks,
+            "gpu_launches": int(launches), "host_issue_ms_per_step": round(host_issue_ms, 3),
+            "loss": round(final_loss, 5), "clocks": clocks,
         }
         for k, v in (("fused_objective", fused), ("roofline", roof), ("roofline_attn", roof_attn), ("roofline_hbm", roof_hbm),
                      ("cpu_baseline", cpu), ("torch_gpu", torch_gpu), ("dp_check", dp_check)):

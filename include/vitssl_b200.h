@@ -68,8 +68,10 @@ int vitssl_profile_read(int64_t index, char* kind_out, int64_t kind_cap, double*
 #define VITSSL_EPI_DGELU 3
 /* The pair the encoder stack uses (feed_forward.py:26-27 and its backward): the forward GEMM saves the
  * whole backward factor instead of the pre-activation, so the backward epilogue is one multiply —
- *   BIAS_GELU_D: u = bf16(acc+bias); C <- dropout(gelu(u)); aux <- mask/(1-p) * gelu'(u)   (bf16)
- *   MUL:         C <- alpha * acc * aux                                                    (bf16) */
+ *   BIAS_GELU_D: u = bf16(acc+bias); C <- dropout(gelu(u)) (bf16); aux <- mask/(1-p) * gelu'(u)
+ *   MUL:         C <- alpha * acc * aux (bf16)
+ * For this pair aux holds IEEE fp16 values (2 bytes, same pitch rules): the factor lies in
+ * [-0.2, 1.2]/(1-p), where fp16's 11 significant bits make the saved copy as good as recomputing. */
 #define VITSSL_EPI_BIAS_GELU_D 4
 #define VITSSL_EPI_MUL 5
 int vitssl_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,

@@ -286,7 +286,7 @@ def test_c_side_profile_records_every_kernel_family_of_the_stack():
     assert len(gemms) == 4 * L + 8 * L                                          # 4 forward + 4 dgrad + 4 wgrad per block
     assert all(ms > 0 and work > 0 for _, ms, work in recs)
     M = 4 * 64
-    assert f"gemm|{M}x256x128|a_mn=0 b_mn=0 epi=2" in kinds and f"gemm|{M}x256x128|a_mn=0 b_mn=1 epi=3" in kinds
+    assert f"gemm|{M}x256x128|a_mn=0 b_mn=0 epi=4" in kinds and f"gemm|{M}x256x128|a_mn=0 b_mn=1 epi=5" in kinds
     assert [k for k, _, _ in lib.profile_collect()] == kinds                   # closed profile: reading again is harmless
     Fb.encoder_stack(blocks, x)                                                 # and nothing is recorded when closed
     lib.profile_begin()

@@ -165,9 +165,9 @@ __device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint
     // the forward (BIAS_GELU_D) — no polynomial, no Philox, no exp in the backward epilogue
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const uint32_t up = u[i >> 1];
+      const float2 f = unpack_f16(u[i >> 1]);  // saved factor: fp16 pairs
       float d0, d1;
-      upk2(fmul2(fmul2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), al), pk2(bf16_lo(up), bf16_hi(up))), d0, d1);
+      upk2(fmul2(fmul2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), al), pk2(f.x, f.y)), d0, d1);
       c[i >> 1] = pack_bf16(d0, d1);
     }
   } else {
@@ -218,7 +218,7 @@ __device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint
           upk2(fmul2(fmul2(uu, scv), cdf), h0, h1);
           upk2(fmul2(gp, scv), g0, g1);
           c[i >> 1] = pack_bf16(h0, h1) & keep[j >> 1];
-          u[i >> 1] = pack_bf16(g0, g1) & keep[j >> 1];
+          u[i >> 1] = pack_f16(g0, g1) & keep[j >> 1];  // fp16: 11 significant bits for a factor in [-0.2, 1.2]/(1-p)
         } else {
           const uint32_t up = u[i >> 1];
           const float u0 = bf16_lo(up), u1 = bf16_hi(up);
@@ -757,14 +757,14 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A,
       v = bf16_round(v);
       e.aux[static_cast<long long>(m) * e.ld_aux + n] = __float2bfloat16_rn(v);
       v = gelu_erf(v);
-    } else if (e.mode == VITSSL_EPI_BIAS_GELU_D) {  // (no dropout on this path)
+    } else if (e.mode == VITSSL_EPI_BIAS_GELU_D) {  // (no dropout on this path); the factor is stored as fp16
       v = bf16_round(v);
-      e.aux[static_cast<long long>(m) * e.ld_aux + n] = __float2bfloat16_rn(gelu_erf_grad(v));
+      reinterpret_cast<__half*>(e.aux)[static_cast<long long>(m) * e.ld_aux + n] = __float2half_rn(gelu_erf_grad(v));
       v = gelu_erf(v);
     } else if (e.mode == VITSSL_EPI_DGELU) {
       v *= gelu_erf_grad(__bfloat162float(e.aux[static_cast<long long>(m) * e.ld_aux + n]));
     } else if (e.mode == VITSSL_EPI_MUL) {
-      v *= __bfloat162float(e.aux[static_cast<long long>(m) * e.ld_aux + n]);
+      v *= __half2float(reinterpret_cast<const __half*>(e.aux)[static_cast<long long>(m) * e.ld_aux + n]);
     }
     if (e.out_fp32)
       reinterpret_cast<float*>(e.c)[static_cast<long long>(m) * e.ldc + n] = v;
