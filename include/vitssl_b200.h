@@ -120,16 +120,21 @@ int vitssl_add_layernorm_bwd_acc(const void* dy, const float* x, int64_t ldx, co
 /* ---- multi-head attention (attention.py:5-27, 86-103) -----------------------------------
  * q/k/v/out are bf16 [B, S, H, 64] views: token rows of pitch ld* elements, head h at column
  * 64*h (so the fused QKV GEMM output is addressed in place). tcgen05 path: d_head = 64,
- * Sk <= 256 (and Sq <= 256 for backward). lse fp32 [B,H,Sq] is saved by forward for backward. */
+ * Sk <= 256 (and Sq <= 256 for backward). lse fp32 [B,H,Sq] is saved by forward for backward.
+ * out_lo (nullable; training) receives bf16(O - bf16(O)) in the layout of `out`: the backward's
+ * delta = rowsum(O * dO) is evaluated from out + out_lo (16 significant bits) because its rounding
+ * error enters dS = P (dP - delta) coherently along a row and, on real activations, dominated the
+ * error of dQ when taken from the bf16 context alone. `delta` is a caller-provided fp32 [B,H,Sq]
+ * workspace that vitssl_attention_bwd fills itself (one extra HBM-bound launch). */
 int vitssl_attention_supported(int64_t Sq, int64_t Sk, int64_t d_head);
 int vitssl_attention_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
-                         int64_t ldv, void* out, int64_t ldo, float* lse, int64_t B, int64_t H,
-                         int64_t Sq, int64_t Sk, float scale, vitssl_stream_t stream);
+                         int64_t ldv, void* out, void* out_lo, int64_t ldo, float* lse, int64_t B,
+                         int64_t H, int64_t Sq, int64_t Sk, float scale, vitssl_stream_t stream);
 int vitssl_attention_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
-                         int64_t ldv, const void* out, const void* d_out, int64_t ldo,
-                         const float* lse, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
-                         int64_t lddv, int64_t B, int64_t H, int64_t Sq, int64_t Sk, float scale,
-                         vitssl_stream_t stream);
+                         int64_t ldv, const void* out, const void* out_lo, const void* d_out,
+                         int64_t ldo, const float* lse, float* delta, void* dq, int64_t lddq, void* dk,
+                         int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H, int64_t Sq,
+                         int64_t Sk, float scale, vitssl_stream_t stream);
 /* generic SIMT attention: any head dim / length, explicit element strides
  * host_strides[12] = {q_b,q_h,q_s, k_b,k_h,k_s, v_b,v_h,v_s, o_b,o_h,o_s}; probs (fp32
  * [B,H,Sq,Sk]) and lse are optional outputs (return_attn=True path, attention.py:24-25).
@@ -150,7 +155,7 @@ int vitssl_attention_generic_bwd(const void* q, const void* k, const void* v,
  * L pre-LN blocks is enqueued from C++, forward or backward, with buffers supplied by the caller.
  * Arrays named `const T* const*` are HOST arrays of L DEVICE pointers. d_head must be 64, S <= 256.
  * Layer l reads the stream from x_in (l = 0) or xs[l]; xs[0] is unused. Saved-for-backward
- * buffers: xs, mean1/rstd1, xn1, qkv ([M,3D]), ctx, lse, xmid, mean2/rstd2, xn2, u, h. In
+ * buffers: xs, mean1/rstd1, xn1, qkv ([M,3D]), ctx, ctx_lo, lse, xmid, mean2/rstd2, xn2, u, h. In
  * inference every layer may point at the same buffers. */
 typedef struct {
   int64_t B, S, D, H, F, L;
@@ -168,6 +173,7 @@ typedef struct {
   const float* const* g1; const float* const* be1; const float* const* g2; const float* const* be2;
   float* const* xs; float* const* mean1; float* const* rstd1; void* const* xn1;
   void* const* qkv; void* const* ctx; float* const* lse;
+  void* const* ctx_lo;            /* bf16 [B*S, D] per layer: rounding residual of ctx (NULL array or NULL entries in inference) */
   float* const* xmid; float* const* mean2; float* const* rstd2; void* const* xn2;
   void* const* u; void* const* h;  /* u: saved GELU backward factor mask/(1-p) * gelu'(pre-activation) */
 } vitssl_encoder_fwd_args;
@@ -178,6 +184,7 @@ typedef struct {
   const float* gout;                   /* fp32 [B*S, D] gradient of `out` */
   float* dx;                           /* fp32 [B*S, D] gradient of x_in */
   void* dbranch; void* du; void* dxn; void* dctx; void* dqkv;  /* bf16 scratch: [M,D] [M,F] [M,D] [M,D] [M,3D] */
+  float* delta;                        /* fp32 scratch [B*H*S]: attention backward row terms */
   float* gs[2];                        /* fp32 [B*S, D] scratch (stream gradient ping-pong) */
   /* parameter gradients: ACCUMULATED into — every buffer below must be zero on entry */
   float* const* dwqkv; float* const* dwo; float* const* dw1; float* const* db1;

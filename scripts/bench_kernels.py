@@ -23,10 +23,10 @@ scale = 1.0 / math.sqrt(64)
 qkv = [(torch.randn(B, S, 3 * D, device=dev) * 0.5).to(bf) for _ in range(NB)]
 dctx = [(torch.randn(B, S, D, device=dev) * 0.5).to(bf) for _ in range(NB)]
 dqkv = [torch.empty(B, S, 3 * D, device=dev, dtype=bf) for _ in range(NB)]
-ctxs, lses = [], []
+ctxs, lses, los = [], [], []
 for i in range(NB):
-    c, l = ops.attention_fwd(qkv[i][..., :D], qkv[i][..., D:2 * D], qkv[i][..., 2 * D:], H, scale)
-    ctxs.append(c); lses.append(l)
+    c, l, lo = ops.attention_fwd(qkv[i][..., :D], qkv[i][..., D:2 * D], qkv[i][..., 2 * D:], H, scale)
+    ctxs.append(c); lses.append(l); los.append(lo)
 xs = [torch.randn(M, D, device=dev) for _ in range(NB)]
 br = [(torch.randn(M, D, device=dev)).to(bf) for _ in range(NB)]
 g, be = torch.randn(D, device=dev), torch.randn(D, device=dev)
@@ -44,7 +44,7 @@ def add(name, fn, work, unit):
 attn_flops = 4.0 * B * H * S * S * 64
 add("attn fwd", lambda i: ops.attention_fwd(qkv[i][..., :D], qkv[i][..., D:2 * D], qkv[i][..., 2 * D:], H, scale), attn_flops, "TFLOP/s")
 add("attn bwd", lambda i: ops.attention_bwd(qkv[i][..., :D], qkv[i][..., D:2 * D], qkv[i][..., 2 * D:], ctxs[i], dctx[i], lses[i], H, scale,
-                                             dqkv[i][..., :D], dqkv[i][..., D:2 * D], dqkv[i][..., 2 * D:]), 2.5 * attn_flops, "TFLOP/s")
+                                             dqkv[i][..., :D], dqkv[i][..., D:2 * D], dqkv[i][..., 2 * D:], out_lo=los[i]), 2.5 * attn_flops, "TFLOP/s")
 add("ln fwd add+ln", lambda i: ops.add_layernorm_fwd(xs[i], br[i], g, be, dropout_p=P, seed=1, offset=0), M * D * 12.0, "GB/s")
 add("ln fwd ln only", lambda i: ops.add_layernorm_fwd(xs[i], None, g, be), M * D * 6.0, "GB/s")
 add("ln bwd full", lambda i: ops.add_layernorm_bwd(br[i], lnout[i][0], lnout[i][2], lnout[i][3], g, xs[i], want_dbranch=True,

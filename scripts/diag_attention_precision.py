@@ -31,9 +31,9 @@ for (B, H, S, std) in [(8, 3, 37, 1.0), (8, 3, 37, 0.3), (12, 6, 37, 1.0), (4, 6
     od.backward(do.double().view(B, S, H, 64).transpose(1, 2))
     ref = [od.transpose(1, 2).reshape(B, S, D)] + [t.grad.transpose(1, 2).reshape(B, S, D) for t in (qd, kd, vd)]
     # (a) tcgen05 kernels
-    ctx, lse = ops.attention_fwd(q, k, v, H, scale)
+    ctx, lse, ctx_lo = ops.attention_fwd(q, k, v, H, scale)
     dqkv = torch.empty_like(qkv)
-    ops.attention_bwd(q, k, v, ctx, do, lse, H, scale, dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:])
+    ops.attention_bwd(q, k, v, ctx, do, lse, H, scale, dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:], out_lo=ctx_lo)
     a = [ctx, dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:]]
     # (b) generic kernels
     qh, kh, vh = (t.unflatten(2, (H, 64)).transpose(1, 2) for t in (q, k, v))

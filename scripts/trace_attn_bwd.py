@@ -11,7 +11,7 @@ bf = torch.bfloat16
 qkv = (torch.randn(B, S, 3 * D, device="cuda") * 0.5).to(bf)
 dctx = (torch.randn(B, S, D, device="cuda") * 0.5).to(bf)
 dqkv = torch.empty_like(qkv)
-ctx, lse = ops.attention_fwd(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], H, 0.125)
+ctx, lse, _lo = ops.attention_fwd(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], H, 0.125)
 for _ in range(3):
     ops.attention_bwd(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], ctx, dctx, lse, H, 0.125,
                       dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:])

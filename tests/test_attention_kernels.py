@@ -36,7 +36,7 @@ def test_attention_tcgen05_fwd_bwd(B, S, H):
     qkv_c = qkv.cuda()
     qv, kv, vv = qkv_c[..., :D], qkv_c[..., D:2 * D], qkv_c[..., 2 * D:]
     scale = 1.0 / math.sqrt(64)
-    out, lse = ops.attention_fwd(qv, kv, vv, H, scale)
+    out, lse, out_lo = ops.attention_fwd(qv, kv, vv, H, scale)
     ref_ctx = ctx_ref.detach().transpose(1, 2).reshape(B, S, D)
     err = (out.double().cpu() - ref_ctx).abs().max().item()
     assert err < 2e-2 * max(1.0, ref_ctx.abs().max().item()), err
@@ -44,9 +44,12 @@ def test_attention_tcgen05_fwd_bwd(B, S, H):
     scores = torch.matmul(q.detach(), k.detach().transpose(-2, -1)) * scale
     assert torch.allclose(lse.double().cpu(), torch.logsumexp(scores, dim=-1), atol=1e-3)
 
+    # hi + lo carries the context to ~16 bits (the backward's delta is evaluated from it)
+    e_hl = ((out.double() + out_lo.double()).cpu() - ref_ctx).abs().max().item()
+    assert e_hl < 1e-2 * max(1.0, ref_ctx.abs().max().item()) and e_hl <= err
     dqkv = torch.empty_like(qkv_c)
     ops.attention_bwd(qv, kv, vv, out, d_out.cuda(), lse, H, scale,
-                      dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:])
+                      dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:], out_lo=out_lo)
     for name, got, ref in (("dq", dqkv[..., :D], q.grad), ("dk", dqkv[..., D:2 * D], k.grad), ("dv", dqkv[..., 2 * D:], v.grad)):
         ref = ref.transpose(1, 2).reshape(B, S, D)
         e = (got.double().cpu() - ref).abs().max().item()
@@ -63,7 +66,7 @@ def test_attention_cross_lengths_tcgen05():
     v = torch.randn(B, Sk, D, generator=g).to(torch.bfloat16)
     qh, kh, vh = [t.double().reshape(B, -1, H, 64).transpose(1, 2) for t in (q, k, v)]
     ref, _ = vit_ref.scaled_dot_product_attention(qh, kh, vh)
-    out, _ = ops.attention_fwd(q.cuda(), k.cuda(), v.cuda(), H, 0.125)
+    out, _, _ = ops.attention_fwd(q.cuda(), k.cuda(), v.cuda(), H, 0.125)
     ref = ref.transpose(1, 2).reshape(B, Sq, D)
     assert (out.double().cpu() - ref).abs().max().item() < 2e-2
 
@@ -84,15 +87,49 @@ def test_attention_bwd_persistent_many_items(B, Sq, Sk, H):
     ref, _ = vit_ref.scaled_dot_product_attention(qh, kh, vh)
     (ref.transpose(1, 2).reshape(B, Sq, D) * d_out.double()).sum().backward()
     qc, kc, vc = q.cuda(), k.cuda(), v.cuda()
-    out, lse = ops.attention_fwd(qc, kc, vc, H, 0.125)
+    out, lse, out_lo = ops.attention_fwd(qc, kc, vc, H, 0.125)
     dq, dk, dv = torch.empty_like(qc), torch.empty_like(kc), torch.empty_like(vc)
     for rep in range(2):  # twice: the second launch must not depend on leftover state
         dq.fill_(7.0); dk.fill_(7.0); dv.fill_(7.0)
-        ops.attention_bwd(qc, kc, vc, out, d_out.cuda(), lse, H, 0.125, dq, dk, dv)
+        ops.attention_bwd(qc, kc, vc, out, d_out.cuda(), lse, H, 0.125, dq, dk, dv, out_lo=out_lo if rep == 0 else None)
         for name, got, r in (("dq", dq, qh.grad), ("dk", dk, kh.grad), ("dv", dv, vh.grad)):
             r = r.transpose(1, 2).reshape(B, -1, D)
             e = (got.double().cpu() - r).abs().max().item()
             assert e < 3e-2 * max(1e-3, r.abs().max().item()), (name, rep, e, r.abs().max().item())
+
+
+@pytest.mark.parametrize("S,H", [(37, 3), (197, 6)])
+def test_attention_bwd_on_tokens_with_a_common_component(S, H):
+    """Real activations: every token's value vector shares a large common part and the upstream
+    gradient sits on one row (a CLS-token loss). Then dP - delta cancels to a small difference and
+    the accuracy of delta = rowsum(O * dO) decides the accuracy of dQ: taken from the bf16 context
+    alone it was ~10x worse than the reference under autocast; from hi + lo it must match it."""
+    ops = _ops()
+    B, D = 6, H * 64
+    g = torch.Generator().manual_seed(S)
+    common = torch.randn(1, 1, 3 * D, generator=g) * 2.0
+    qkv = (common + 0.5 * torch.randn(B, S, 3 * D, generator=g)).to(torch.bfloat16)
+    d_out = torch.zeros(B, S, D)
+    d_out[:, 0] = torch.randn(B, D, generator=g) * 0.02
+    d_out = d_out.to(torch.bfloat16)
+    q, k, v, ctx_ref, _ = _ref(qkv, B, S, H)
+    (ctx_ref.transpose(1, 2).reshape(B, S, D) * d_out.double()).sum().backward()
+    qkv_c = qkv.cuda()
+    qv, kv, vv = qkv_c[..., :D], qkv_c[..., D:2 * D], qkv_c[..., 2 * D:]
+    out, lse, out_lo = ops.attention_fwd(qv, kv, vv, H, 0.125)
+    dqkv = torch.empty_like(qkv_c)
+    ops.attention_bwd(qv, kv, vv, out, d_out.cuda(), lse, H, 0.125, dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:], out_lo=out_lo)
+    # the reference's arithmetic under autocast on the same inputs (attention.py:20-23), as the yardstick
+    qt, kt, vt = (t.view(B, S, H, 64).transpose(1, 2).detach().clone().requires_grad_(True) for t in (qv, kv, vv))
+    pr = torch.softmax(((qt @ kt.transpose(-1, -2)) / 8.0).float(), -1)
+    (pr.to(torch.bfloat16) @ vt).backward(d_out.cuda().view(B, S, H, 64).transpose(1, 2))
+
+    def rl2(a, b):
+        return ((a.double().cpu() - b).norm() / b.norm()).item()
+    for name, got, yard, ref in (("dq", dqkv[..., :D], qt.grad, q.grad), ("dk", dqkv[..., D:2 * D], kt.grad, k.grad), ("dv", dqkv[..., 2 * D:], vt.grad, v.grad)):
+        ref = ref.transpose(1, 2).reshape(B, S, D)
+        e, ey = rl2(got, ref), rl2(yard.transpose(1, 2).reshape(B, S, D), ref)
+        assert e <= max(1e-2, 2.0 * ey), (name, e, ey)
 
 
 @pytest.mark.parametrize("B,H,Sq,Sk,d", [(4, 1, 10, 10, 10), (4, 8, 10, 12, 8), (2, 6, 300, 300, 64), (3, 4, 17, 17, 32)])

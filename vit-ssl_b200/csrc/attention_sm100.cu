@@ -26,6 +26,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // ------------------------------------------------------------------------------------------
 struct AttnFwdParams {
   __nv_bfloat16* out; long long ldo;  // context [B*Sq, ldo]; head h occupies cols [64h, 64h+64)
+  __nv_bfloat16* out_lo;              // nullable, same layout: bf16(O - bf16(O)), see attn_delta_kernel
   float* lse;                         // [B, H, Sq] log-sum-exp of the scaled scores
   int B, H, Sq, Sk, kv_rows;          // kv_rows = round_up(Sk, 16) <= 256
   float scale;
@@ -231,25 +232,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_oread);  // O is in registers: the next item's S MMA may overwrite TMEM
         if (qrow < p.Sq) {
-          __nv_bfloat16* op = p.out + (static_cast<long long>(b) * p.Sq + qrow) * p.ldo + h * 64;
+          const long long ooff = (static_cast<long long>(b) * p.Sq + qrow) * p.ldo + h * 64;
+          __nv_bfloat16* op = p.out + ooff;
+          // 8 context values -> 16 bytes of bf16, and (training) 16 bytes of their bf16 rounding
+          // residuals: hi + lo carries 16 significant bits of O, which the backward's
+          // delta = rowsum(O * dO) needs (attn_delta_kernel)
+          auto emit8 = [&](const uint32_t (&r)[32], int i, int col) {
+            float x[8];
+            uint32_t hi[4];
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(r0[i]) * inv, __uint_as_float(r0[i + 1]) * inv);
-            o.y = pack_bf16(__uint_as_float(r0[i + 2]) * inv, __uint_as_float(r0[i + 3]) * inv);
-            o.z = pack_bf16(__uint_as_float(r0[i + 4]) * inv, __uint_as_float(r0[i + 5]) * inv);
-            o.w = pack_bf16(__uint_as_float(r0[i + 6]) * inv, __uint_as_float(r0[i + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + i) = o;
-          }
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(r[i + e]) * inv;
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(r1[i]) * inv, __uint_as_float(r1[i + 1]) * inv);
-            o.y = pack_bf16(__uint_as_float(r1[i + 2]) * inv, __uint_as_float(r1[i + 3]) * inv);
-            o.z = pack_bf16(__uint_as_float(r1[i + 4]) * inv, __uint_as_float(r1[i + 5]) * inv);
-            o.w = pack_bf16(__uint_as_float(r1[i + 6]) * inv, __uint_as_float(r1[i + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + 32 + i) = o;
-          }
+            for (int e = 0; e < 4; ++e) hi[e] = pack_bf16(x[2 * e], x[2 * e + 1]);
+            *reinterpret_cast<uint4*>(op + col) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (p.out_lo) {
+              uint32_t lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) lo[e] = pack_bf16(x[2 * e] - bf16_lo(hi[e]), x[2 * e + 1] - bf16_hi(hi[e]));
+              *reinterpret_cast<uint4*>(p.out_lo + ooff + col) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          };
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) emit8(r0, i, i);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) emit8(r1, i, 32 + i);
           if (p.lse)
             p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qrow] = mx * p.scale + __logf(sum);
         }
@@ -268,8 +274,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // backward
 // ------------------------------------------------------------------------------------------
 struct AttnBwdParams {
-  const __nv_bfloat16* o; const __nv_bfloat16* d_o; long long ldo;  // [B*Sq, ldo]
   const float* lse;                                                 // [B,H,Sq]
+  const float* delta;                                               // [B,H,Sq] rowsum(O * dO), attn_delta_kernel
   __nv_bfloat16* dq; long long lddq;                                // [B*Sq, lddq]
   __nv_bfloat16* dk; long long lddk;                                // [B*Sk, lddk]
   __nv_bfloat16* dv; long long lddv;
@@ -325,7 +331,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_dq,
+                const __grid_constant__ CUtensorMap tmap_dq,
                 const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
                 const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -357,7 +363,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == BWD_WARP_TMA) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k);
-      tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_o);
+      tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
       tma_prefetch_desc(&tmap_dq); tma_prefetch_desc(&tmap_dk); tma_prefetch_desc(&tmap_dv);
       for (int i = 0; i < 8; ++i) mbar_init(bar + i, 1);
       mbar_init(bar_sdp_full, 1); mbar_init(bar_sdp_read, BWD_MATH_WARPS);
@@ -400,10 +406,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         auto load_q = [&](int i) {
           const int sl = alt ? (n & 1) : i;
           if (u > 0) mbar_wait_parked(&bar_freeq[sl], (u - 1) & 1);
-          mbar_expect_tx(&bar_ldq[sl], 3 * BWD_TILE);
+          mbar_expect_tx(&bar_ldq[sl], 2 * BWD_TILE);
           tma_load_3d(smem + BWD_SMEM_Q + sl * BWD_TILE, &tmap_q, &bar_ldq[sl], h * 64, i * 128, b);
           tma_load_3d(smem + BWD_SMEM_DO + sl * BWD_TILE, &tmap_do, &bar_ldq[sl], h * 64, i * 128, b);
-          tma_load_3d(smem + BWD_SMEM_O + sl * BWD_TILE, &tmap_o, &bar_ldq[sl], h * 64, i * 128, b);
         };
         // in the order the slots are released by the previous item and first needed by this one
         load_kv(0);
@@ -572,48 +577,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       asm volatile("bar.sync 1, %0;" ::"n"(32 * BWD_MATH_WARPS) : "memory");  // ... by any math warp
     };
 
-    // -lse * log2(e) of this thread's two query rows; the next item's values are fetched during
-    // the current item's last iteration
+    // -lse * log2(e) and delta = rowsum(O * dO) of this thread's two query rows ([B, H, Sq] = [item, Sq]
+    // arrays; delta comes from attn_delta_kernel, which evaluates it from the hi + lo context so that
+    // its error stays far below the (dP - delta) cancellation it enters); the next item's values are
+    // fetched during the current item's last iteration
     auto load_nlse = [&](int item, int i) {
       const int qrow = i * 128 + r;
       return (i < nq && qrow < p.Sq) ? -p.lse[static_cast<long long>(item) * p.Sq + qrow] * kLog2e : -INFINITY;
     };
-    float nx0 = 0.f, nx1 = 0.f;
-    if (blockIdx.x < items) { nx0 = load_nlse(blockIdx.x, 0); nx1 = load_nlse(blockIdx.x, 1); }
+    auto load_delta = [&](int item, int i) {
+      const int qrow = i * 128 + r;
+      return (i < nq && qrow < p.Sq) ? p.delta[static_cast<long long>(item) * p.Sq + qrow] : 0.f;
+    };
+    float nx0 = 0.f, nx1 = 0.f, nd0 = 0.f, nd1 = 0.f;
+    if (blockIdx.x < items) {
+      nx0 = load_nlse(blockIdx.x, 0); nx1 = load_nlse(blockIdx.x, 1);
+      nd0 = load_delta(blockIdx.x, 0); nd1 = load_delta(blockIdx.x, 1);
+    }
 
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
-      float delta0 = 0.f, delta1 = 0.f;
-      const float nlse0 = nx0, nlse1 = nx1;  // lse is [B, H, Sq] = [item, Sq]; -inf on invalid rows -> p = 0
+      const float delta0 = nd0, delta1 = nd1;
+      const float nlse0 = nx0, nlse1 = nx1;  // -inf on invalid rows -> p = 0
       for (int it = 0; it < nit; ++it, ++g) {
         const int j = it_j(it), i = it_i(it);
         if (it == nit - 1 && item + static_cast<int>(gridDim.x) < items) {
           nx0 = load_nlse(item + gridDim.x, 0);
           nx1 = load_nlse(item + gridDim.x, 1);
-        }
-        if (j == 0) {
-          // first use of query tile i: delta_i = sum_d O[i, d] * dO[i, d] from the staged tiles
-          const int slq = alt ? (n & 1) : i;
-          mbar_wait_parked_addr(sbar + 8 * slq, (alt ? n >> 1 : n) & 1);  // bar_ldq[slq]
-          float dl = 0.f;
-          if (i * 128 + r < p.Sq) {
-            const uint32_t so = sbase + BWD_SMEM_O + slq * BWD_TILE + r * 128;
-            const uint32_t sd = sbase + BWD_SMEM_DO + slq * BWD_TILE + r * 128;
-            f32x2 acc2 = pk2(0.f, 0.f);
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              const int sw = (v ^ (r & 7)) << 4;
-              const uint4 a = lds128(so + sw);
-              const uint4 d = lds128(sd + sw);
-              acc2 = ffma2(pk2(bf16_lo(a.x), bf16_hi(a.x)), pk2(bf16_lo(d.x), bf16_hi(d.x)), acc2);
-              acc2 = ffma2(pk2(bf16_lo(a.y), bf16_hi(a.y)), pk2(bf16_lo(d.y), bf16_hi(d.y)), acc2);
-              acc2 = ffma2(pk2(bf16_lo(a.z), bf16_hi(a.z)), pk2(bf16_lo(d.z), bf16_hi(d.z)), acc2);
-              acc2 = ffma2(pk2(bf16_lo(a.w), bf16_hi(a.w)), pk2(bf16_lo(d.w), bf16_hi(d.w)), acc2);
-            }
-            float a0, a1;
-            upk2(acc2, a0, a1);
-            dl = a0 + a1;
-          }
-          if (i == 0) delta0 = dl; else delta1 = dl;
+          nd0 = load_delta(item + gridDim.x, 0);
+          nd1 = load_delta(item + gridDim.x, 1);
         }
         if (threadIdx.x == 0) TRACE(16 * g + 8);
         mbar_wait_parked_addr(sbar + 8 * 8, g & 1);  // bar_sdp_full
@@ -714,6 +705,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == BWD_WARP_TMA) {
     tc_fence_after();
     tmem_dealloc<512>(0u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// delta[b, h, s] = sum_d O[b, s, h, d] * dO[b, s, h, d] — the row term of the softmax backward,
+// dS = P * (dP - delta). The backward kernel used to take it from the bf16 context tiles; on real
+// activations (tokens share a large common component, so dP - delta cancels to a small difference)
+// the 2^-9 rounding of O then dominates the error of dQ: measured 4.8e-2 relative on a late ViT-Ti
+// block against 5e-3 for the reference under autocast. The forward therefore also stores the bf16
+// rounding residual of the context; O = hi + lo has 16 significant bits and the same case measures
+// 8.5e-3 (4.3e-3 is the floor of this formulation). HBM-bound: 6 bytes per context element.
+// One warp per token row, 8 elements per lane per step; a head is 8 consecutive lanes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                         const __nv_bfloat16* __restrict__ o_lo,
+                                                         const __nv_bfloat16* __restrict__ d_o, long long ldo,
+                                                         float* __restrict__ delta, long long rows, int H, int S) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long b = row / S;
+  const int sidx = static_cast<int>(row - b * S);
+  const int groups = H * 8;
+  for (int g0 = 0; g0 < groups; g0 += 32) {
+    const int g = g0 + lane;
+    float acc = 0.f;
+    if (g < groups) {
+      const long long off = row * ldo + g * 8;
+      const uint4 a = *reinterpret_cast<const uint4*>(o + off);
+      const uint4 d = *reinterpret_cast<const uint4*>(d_o + off);
+      uint4 l = make_uint4(0u, 0u, 0u, 0u);
+      if (o_lo) l = *reinterpret_cast<const uint4*>(o_lo + off);
+      f32x2 acc2 = pk2(0.f, 0.f);
+      acc2 = ffma2(fadd2(pk2(bf16_lo(a.x), bf16_hi(a.x)), pk2(bf16_lo(l.x), bf16_hi(l.x))), pk2(bf16_lo(d.x), bf16_hi(d.x)), acc2);
+      acc2 = ffma2(fadd2(pk2(bf16_lo(a.y), bf16_hi(a.y)), pk2(bf16_lo(l.y), bf16_hi(l.y))), pk2(bf16_lo(d.y), bf16_hi(d.y)), acc2);
+      acc2 = ffma2(fadd2(pk2(bf16_lo(a.z), bf16_hi(a.z)), pk2(bf16_lo(l.z), bf16_hi(l.z))), pk2(bf16_lo(d.z), bf16_hi(d.z)), acc2);
+      acc2 = ffma2(fadd2(pk2(bf16_lo(a.w), bf16_hi(a.w)), pk2(bf16_lo(l.w), bf16_hi(l.w))), pk2(bf16_lo(d.w), bf16_hi(d.w)), acc2);
+      float a0, a1;
+      upk2(acc2, a0, a1);
+      acc = a0 + a1;
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (g < groups && (lane & 7) == 0) delta[(b * H + (g >> 3)) * S + sidx] = acc;
   }
 }
 
@@ -862,7 +900,7 @@ extern "C" int vitssl_attention_supported(int64_t Sq, int64_t Sk, int64_t d_head
 }
 
 extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v, int64_t ldq,
-                                    int64_t ldk, int64_t ldv, void* out, int64_t ldo, float* lse,
+                                    int64_t ldk, int64_t ldv, void* out, void* out_lo, int64_t ldo, float* lse,
                                     int64_t B, int64_t H, int64_t Sq, int64_t Sk, float scale,
                                     cudaStream_t stream) {
   VITSSL_REQUIRE(q && k && v && out, VITSSL_ERR_ARG, "attention_fwd: null pointer");
@@ -874,7 +912,8 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
   VITSSL_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
                  ((uintptr_t)out % 16 == 0), VITSSL_ERR_ARG, "attention_fwd: pointers must be 16-byte aligned");
   AttnFwdParams p{};
-  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.lse = lse;
+  VITSSL_REQUIRE(out_lo == nullptr || (uintptr_t)out_lo % 16 == 0, VITSSL_ERR_ARG, "attention_fwd: out_lo must be 16-byte aligned");
+  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo; p.lse = lse;
   p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk;
   p.kv_rows = (int)((Sk + 15) / 16 * 16); p.scale = scale;
   CUtensorMap mq, mk, mv;
@@ -897,30 +936,40 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
 }
 
 extern "C" int vitssl_attention_bwd(const void* q, const void* k, const void* v, int64_t ldq,
-                                    int64_t ldk, int64_t ldv, const void* out, const void* d_out,
-                                    int64_t ldo, const float* lse, void* dq, int64_t lddq, void* dk,
+                                    int64_t ldk, int64_t ldv, const void* out, const void* out_lo, const void* d_out,
+                                    int64_t ldo, const float* lse, float* delta, void* dq, int64_t lddq, void* dk,
                                     int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
                                     int64_t Sq, int64_t Sk, float scale, cudaStream_t stream) {
-  VITSSL_REQUIRE(q && k && v && out && d_out && lse && dq && dk && dv, VITSSL_ERR_ARG, "attention_bwd: null pointer");
+  VITSSL_REQUIRE(q && k && v && out && d_out && lse && delta && dq && dk && dv, VITSSL_ERR_ARG, "attention_bwd: null pointer");
+  VITSSL_REQUIRE(((uintptr_t)out % 16 == 0) && ((uintptr_t)d_out % 16 == 0) && ((uintptr_t)out_lo % 16 == 0), VITSSL_ERR_ARG,
+                 "attention_bwd: out / out_lo / d_out must be 16-byte aligned");
   VITSSL_REQUIRE(B > 0 && H > 0 && Sq > 0 && Sk > 0 && Sk <= 256 && Sq <= 256, VITSSL_ERR_SHAPE,
                  "attention_bwd: unsupported shape Sq=%lld Sk=%lld (tcgen05 path needs both <= 256)",
                  (long long)Sq, (long long)Sk);
   VITSSL_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0 &&
                  lddk % 8 == 0 && lddv % 8 == 0, VITSSL_ERR_SHAPE, "attention_bwd: row pitches must be multiples of 8");
   AttnBwdParams p{};
-  p.o = reinterpret_cast<const __nv_bfloat16*>(out); p.d_o = reinterpret_cast<const __nv_bfloat16*>(d_out);
-  p.ldo = ldo; p.lse = lse;
+  p.lse = lse; p.delta = delta;
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.lddq = lddq;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.lddk = lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.lddv = lddv;
   p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk; p.scale = scale;
-  CUtensorMap mq, mk, mv, mdo, mo;
+  {
+    // delta = rowsum(O * dO) per (batch, head, query) from the hi (+ lo) context: a small HBM-bound pass
+    const long long rows = (long long)B * Sq;
+    cudaError_t derr = launch_pdl(attn_delta_kernel, dim3((unsigned)((rows + 3) / 4)), dim3(128), 0, stream,
+                                  reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(out_lo),
+                                  reinterpret_cast<const __nv_bfloat16*>(d_out), (long long)ldo, delta, rows, (int)H, (int)Sq);
+    if (derr != cudaSuccess) { set_error("attention_bwd: delta launch failed: %s", cudaGetErrorString(derr)); return VITSSL_ERR_CUDA; }
+    const int rc0 = check_launch("attention_delta");
+    if (rc0) return rc0;
+  }
+  CUtensorMap mq, mk, mv, mdo;
   int rc;
   if ((rc = make_head_map(&mq, q, p.B, p.Sq, p.H, ldq, 128))) return rc;
   if ((rc = make_head_map(&mk, k, p.B, p.Sk, p.H, ldk, 128))) return rc;
   if ((rc = make_head_map(&mv, v, p.B, p.Sk, p.H, ldv, 128))) return rc;
   if ((rc = make_head_map(&mdo, d_out, p.B, p.Sq, p.H, ldo, 128))) return rc;
-  if ((rc = make_head_map(&mo, out, p.B, p.Sq, p.H, ldo, 128))) return rc;
   // outputs leave through 32-column x 32-row staging blocks (64-byte swizzle), clipped at S
   CUtensorMap mdq, mdk, mdv;
   auto out_map = [&](CUtensorMap* m, void* base, int S, long long ld) {
@@ -938,7 +987,7 @@ extern "C" int vitssl_attention_bwd(const void* q, const void* k, const void* v,
   }
   const long long items = (long long)B * H;  // persistent: one CTA per SM walks the (batch, head) items
   const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
-  cudaError_t lerr = launch_pdl(attn_bwd_kernel, dim3(grid), dim3(BWD_THREADS), BWD_SMEM_BYTES, stream, mq, mk, mv, mdo, mo,
+  cudaError_t lerr = launch_pdl(attn_bwd_kernel, dim3(grid), dim3(BWD_THREADS), BWD_SMEM_BYTES, stream, mq, mk, mv, mdo,
                                 mdq, mdk, mdv, p);
   if (lerr != cudaSuccess) { set_error("attention_bwd: launch failed: %s", cudaGetErrorString(lerr)); return VITSSL_ERR_CUDA; }
   return check_launch("attention_bwd");

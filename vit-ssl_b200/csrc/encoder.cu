@@ -65,8 +65,9 @@ extern "C" int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* a, cudaSt
                                   nullptr, nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(a->qkv[l]);
     VITSSL_TIMED("attn_fwd", attn_flops(B, H, S),
-                 vitssl_attention_fwd(qkv, qkv + D, qkv + 2 * D, 3 * D, 3 * D, 3 * D, a->ctx[l], D, a->lse[l], B, H, S,
-                                      S, scale, stream));                     // attention.py:20-23
+                 vitssl_attention_fwd(qkv, qkv + D, qkv + 2 * D, 3 * D, 3 * D, 3 * D, a->ctx[l],
+                                      a->ctx_lo ? a->ctx_lo[l] : nullptr, D, a->lse[l], B, H, S, S, scale,
+                                      stream));                               // attention.py:20-23
     VITSSL_TIMED(gemm_kind(M, D, D, 0, 0, 0).s, gemm_flops(M, D, D),
                  vitssl_gemm_bf16(a->ctx[l], a->wo[l], a->y1, M, D, D, D, D, D, 0, 0, VITSSL_EPI_NONE, nullptr,
                                   nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));  // attention.py:105
@@ -93,7 +94,8 @@ extern "C" int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* a, cudaSt
 }
 
 extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaStream_t stream) {
-  VITSSL_REQUIRE(a != nullptr && a->fwd != nullptr && a->fwd->L >= 1, VITSSL_ERR_ARG, "encoder_stack_bwd: bad args");
+  VITSSL_REQUIRE(a != nullptr && a->fwd != nullptr && a->fwd->L >= 1 && a->delta != nullptr, VITSSL_ERR_ARG,
+                 "encoder_stack_bwd: bad args");
   const vitssl_encoder_fwd_args* f = a->fwd;
   const int64_t B = f->B, S = f->S, D = f->D, H = f->H, F = f->F, L = f->L;
   const int64_t M = B * S;
@@ -155,8 +157,9 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(f->qkv[l]);
     __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv);
     VITSSL_TIMED("attn_bwd", 2.5 * attn_flops(B, H, S),
-                 vitssl_attention_bwd(qkv, qkv + D, qkv + 2 * D, 3 * D, 3 * D, 3 * D, f->ctx[l], a->dctx, D, f->lse[l],
-                                      dqkv, 3 * D, dqkv + D, 3 * D, dqkv + 2 * D, 3 * D, B, H, S, S, scale, stream));
+                 vitssl_attention_bwd(qkv, qkv + D, qkv + 2 * D, 3 * D, 3 * D, 3 * D, f->ctx[l],
+                                      f->ctx_lo ? f->ctx_lo[l] : nullptr, a->dctx, D, f->lse[l], a->delta, dqkv, 3 * D,
+                                      dqkv + D, 3 * D, dqkv + 2 * D, 3 * D, B, H, S, S, scale, stream));
     VITSSL_TIMED(gemm_kind(M, D, 3 * D, 0, 1, 0).s, gemm_flops(M, D, 3 * D),
                  vitssl_gemm_bf16(dqkv, f->wqkv[l], a->dxn, M, D, 3 * D, 3 * D, D, D, 0, 1, VITSSL_EPI_NONE, nullptr,
                                   nullptr, 0, 1.0f, 0, 0, 0.f, 0, 0, stream));

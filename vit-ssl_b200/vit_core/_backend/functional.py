@@ -135,7 +135,8 @@ def autocast_out(y: torch.Tensor) -> torch.Tensor:
 # attention core shared by the encoder stack and MultiHeadedAttention
 # ----------------------------------------------------------------------------------------
 def _attn_fwd(q, k, v, H, want_lse):
-    """q: [B,Sq,D] bf16 view, k/v: [B,Sk,D] views (unit inner stride). Returns (ctx [B,Sq,D], lse)."""
+    """q: [B,Sq,D] bf16 view, k/v: [B,Sk,D] views (unit inner stride). Returns (ctx [B,Sq,D], lse,
+    ctx_lo): ctx_lo (tcgen05 path, training) is the bf16 rounding residual of ctx for the backward."""
     B, Sq, D = q.shape
     Sk = k.shape[1]
     dk = D // H
@@ -144,16 +145,16 @@ def _attn_fwd(q, k, v, H, want_lse):
         return ops.attention_fwd(q, k, v, H, scale, want_lse=want_lse)
     qh, kh, vh = (t.unflatten(2, (H, dk)).transpose(1, 2) for t in (q, k, v))
     out, _, lse = ops.attention_generic_fwd(qh, kh, vh, scale, want_probs=False, want_lse=want_lse)
-    return out.transpose(1, 2).reshape(B, Sq, D), lse
+    return out.transpose(1, 2).reshape(B, Sq, D), lse, None
 
 
-def _attn_bwd(q, k, v, ctx_, dctx, lse, H, dq, dk_, dv):
+def _attn_bwd(q, k, v, ctx_, dctx, lse, H, dq, dk_, dv, ctx_lo=None):
     B, Sq, D = q.shape
     Sk = k.shape[1]
     dk = D // H
     scale = 1.0 / math.sqrt(dk)
     if ops.attention_supported(Sq, Sk, dk) and Sq <= 256:
-        ops.attention_bwd(q, k, v, ctx_, dctx, lse, H, scale, dq, dk_, dv)
+        ops.attention_bwd(q, k, v, ctx_, dctx, lse, H, scale, dq, dk_, dv, out_lo=ctx_lo)
         return
     qh, kh, vh = (t.unflatten(2, (H, dk)).transpose(1, 2) for t in (q, k, v))
     oh = ctx_.unflatten(2, (H, dk)).transpose(1, 2)
@@ -220,7 +221,7 @@ class _EncoderStackFn(torch.autograd.Function):
                 offset=max(3 * l - 1, 0))
             qkv = ops.gemm(xn1, wqkv)
             qkv3 = qkv.view(B, S, 3 * D)
-            ctx_, lse = _attn_fwd(qkv3[..., :D], qkv3[..., D:2 * D], qkv3[..., 2 * D:], H, need_grad)
+            ctx_, lse, ctx_lo = _attn_fwd(qkv3[..., :D], qkv3[..., D:2 * D], qkv3[..., 2 * D:], H, need_grad)
             y1 = ops.gemm(ctx_.view(M, D), wo)
             xmid, xn2, mean2, rstd2 = ops.add_layernorm_fwd(xs, y1, g2, be2, dropout_p=p, seed=seed,
                                                             offset=3 * l)
@@ -231,7 +232,7 @@ class _EncoderStackFn(torch.autograd.Function):
             stream, branch = xmid, y2
             last_qkv = qkv3
             if need_grad:
-                saved.append((xs, mean1, rstd1, xn1, qkv3, ctx_, lse, xmid, mean2, rstd2, xn2, u, h))
+                saved.append((xs, mean1, rstd1, xn1, qkv3, ctx_, lse, xmid, mean2, rstd2, xn2, u, h, ctx_lo))
         out, _, _, _ = ops.add_layernorm_fwd(stream, branch, None, None, dropout_p=p, seed=seed,
                                              offset=3 * L - 1)
         probs = None
@@ -286,7 +287,7 @@ class _EncoderStackFn(torch.autograd.Function):
         for l in reversed(range(L)):
             wqkv, wo, w1, w2 = meta.weights[l]
             g1, g2 = params[12 * l + 8], params[12 * l + 10]
-            xs, mean1, rstd1, xn1, qkv3, ctx_, lse, xmid, mean2, rstd2, xn2, u, h = saved[l]
+            xs, mean1, rstd1, xn1, qkv3, ctx_, lse, xmid, mean2, rstd2, xn2, u, h, ctx_lo = saved[l]
             saved[l] = None
             dy2 = dbranch
             du = ops.gemm(dy2, w2, b_mn=True, epilogue=EPI_MUL, aux=u)
@@ -303,7 +304,7 @@ class _EncoderStackFn(torch.autograd.Function):
             dWo = ops.gemm(dy1, ctx_.view(M, D), a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
             dqkv = torch.empty((B, S, 3 * D), device=g.device, dtype=torch.bfloat16)
             _attn_bwd(qkv3[..., :D], qkv3[..., D:2 * D], qkv3[..., 2 * D:], ctx_, dctx.view(B, S, D), lse, H,
-                      dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:])
+                      dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:], ctx_lo=ctx_lo)
             dqkv2 = dqkv.view(M, 3 * D)
             dxn1 = ops.gemm(dqkv2, wqkv, b_mn=True)
             dWqkv = ops.gemm(dqkv2, xn1, a_mn=True, b_mn=True, out_dtype=torch.float32, split_k=-1)
@@ -539,10 +540,10 @@ class _MHAFn(torch.autograd.Function):
             q = ops.gemm(qb, wqkv[:D]).view(B, Sq, D)
             k = ops.gemm(kb, wqkv[D:2 * D]).view(B, Sk, D)
             v = ops.gemm(vb, wqkv[2 * D:]).view(B, Sk, D)
-        ctx_, lse = _attn_fwd(q, k, v, H, True)
+        ctx_, lse, ctx_lo = _attn_fwd(q, k, v, H, True)
         out = ops.gemm(ctx_.view(-1, D), wob).view(B, Sq, D)
         probs = attention_probs(q, k, H) if meta.return_attn else None
-        ctx.saved = (qb, kb, vb, q, k, v, ctx_, lse)
+        ctx.saved = (qb, kb, vb, q, k, v, ctx_, lse, ctx_lo)
         ctx.meta = meta
         ctx.in_dtype = q_in.dtype
         if probs is not None:
@@ -554,7 +555,7 @@ class _MHAFn(torch.autograd.Function):
     def backward(ctx, gout, *_):
         meta = ctx.meta
         H = meta.H
-        qb, kb, vb, q, k, v, ctx_, lse = ctx.saved
+        qb, kb, vb, q, k, v, ctx_, lse, ctx_lo = ctx.saved
         wqkv, wob = meta.weights
         B, Sq, D = q.shape
         Sk = k.shape[1]
@@ -564,7 +565,7 @@ class _MHAFn(torch.autograd.Function):
         f32 = torch.float32
         if meta.same:
             dqkv = torch.empty((B, Sq, 3 * D), device=dy.device, dtype=torch.bfloat16)
-            _attn_bwd(q, k, v, ctx_, dctx, lse, H, dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:])
+            _attn_bwd(q, k, v, ctx_, dctx, lse, H, dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:], ctx_lo=ctx_lo)
             d2 = dqkv.view(-1, 3 * D)
             dx = ops.gemm(d2, wqkv, b_mn=True, out_dtype=f32).view(B, Sq, D)
             dW = ops.gemm(d2, qb, a_mn=True, b_mn=True, out_dtype=f32, split_k=-1)
@@ -573,7 +574,7 @@ class _MHAFn(torch.autograd.Function):
         dq = torch.empty((B, Sq, D), device=dy.device, dtype=torch.bfloat16)
         dk = torch.empty((B, Sk, D), device=dy.device, dtype=torch.bfloat16)
         dv = torch.empty((B, Sk, D), device=dy.device, dtype=torch.bfloat16)
-        _attn_bwd(q, k, v, ctx_, dctx, lse, H, dq, dk, dv)
+        _attn_bwd(q, k, v, ctx_, dctx, lse, H, dq, dk, dv, ctx_lo=ctx_lo)
         outs = []
         for g_, w_, xb_, S_ in ((dq, wqkv[:D], qb, Sq), (dk, wqkv[D:2 * D], kb, Sk), (dv, wqkv[2 * D:], vb, Sk)):
             g2 = g_.view(-1, D)

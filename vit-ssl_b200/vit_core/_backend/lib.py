@@ -34,8 +34,8 @@ SIGNATURES["vitssl_add_layernorm_fwd"] = "plpp" + "pp" + "ppp" + "ll" + "ff" + "
 SIGNATURES["vitssl_add_layernorm_bwd"] = "ppl" + "ppp" + "pl" + "pl" + "p" + "pp" + "ll" + "f" + "uu" + "s"
 SIGNATURES["vitssl_add_layernorm_bwd_acc"] = SIGNATURES["vitssl_add_layernorm_bwd"]
 SIGNATURES["vitssl_attention_supported"] = "lll"
-SIGNATURES["vitssl_attention_fwd"] = "ppp" + "lll" + "pl" + "p" + "llll" + "f" + "s"
-SIGNATURES["vitssl_attention_bwd"] = "ppp" + "lll" + "ppl" + "p" + "pl" + "pl" + "pl" + "llll" + "f" + "s"
+SIGNATURES["vitssl_attention_fwd"] = "ppp" + "lll" + "ppl" + "p" + "llll" + "f" + "s"
+SIGNATURES["vitssl_attention_bwd"] = "ppp" + "lll" + "pppl" + "pp" + "pl" + "pl" + "pl" + "llll" + "f" + "s"
 SIGNATURES["vitssl_attention_generic_fwd"] = "ppp" + "p" + "ppp" + "lllll" + "f" + "s"
 SIGNATURES["vitssl_attention_generic_bwd"] = "ppp" + "p" + "pp" + "p" + "ppp" + "lllll" + "f" + "s"
 SIGNATURES["vitssl_encoder_stack_fwd"] = "ps"

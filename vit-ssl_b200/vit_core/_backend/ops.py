@@ -186,7 +186,9 @@ def attention_supported(Sq, Sk, d):
 
 
 def attention_fwd(q, k, v, H, scale, want_lse=True):
-    """q: bf16 [B,Sq,H*64] view (last dim contiguous, token pitch uniform); k,v likewise."""
+    """q: bf16 [B,Sq,H*64] view (last dim contiguous, token pitch uniform); k,v likewise.
+    Returns (out bf16 [B,Sq,H*64], lse | None, out_lo | None): out_lo = bf16(O - bf16(O)) is produced with
+    the LSE (training) and goes to `attention_bwd`, whose delta = rowsum(O * dO) needs O to 16 bits."""
     _l.ensure_device()
     B, Sq, _ = q.shape
     Sk = k.shape[1]
@@ -194,20 +196,23 @@ def attention_fwd(q, k, v, H, scale, want_lse=True):
         assert t_.dtype == torch.bfloat16 and t_.stride(2) == 1 and t_.stride(0) == S_ * t_.stride(1)
     out = torch.empty((B, Sq, H * 64), device=q.device, dtype=torch.bfloat16)
     lse = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32) if want_lse else None
+    out_lo = torch.empty_like(out) if want_lse else None
     _l.call("vitssl_attention_fwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), v.stride(1),
-            _p(out), out.stride(1), _p(lse), B, H, Sq, Sk, float(scale), _l.stream_ptr())
-    return out, lse
+            _p(out), _p(out_lo), out.stride(1), _p(lse), B, H, Sq, Sk, float(scale), _l.stream_ptr())
+    return out, lse, out_lo
 
 
-def attention_bwd(q, k, v, out, d_out, lse, H, scale, dq, dk, dv):
+def attention_bwd(q, k, v, out, d_out, lse, H, scale, dq, dk, dv, out_lo=None):
     """dq/dk/dv: preallocated bf16 [B,S,H*64] views (may alias slices of one [B,S,3D] buffer)."""
     _l.ensure_device()
     B, Sq, _ = q.shape
     Sk = k.shape[1]
     assert out.is_contiguous() and d_out.is_contiguous() and d_out.dtype == torch.bfloat16
+    assert out_lo is None or (out_lo.is_contiguous() and out_lo.shape == out.shape and out_lo.dtype == torch.bfloat16)
+    delta = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32)
     _l.call("vitssl_attention_bwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), v.stride(1),
-            _p(out), _p(d_out), out.stride(1), _p(lse), _p(dq), dq.stride(1), _p(dk), dk.stride(1),
-            _p(dv), dv.stride(1), B, H, Sq, Sk, float(scale), _l.stream_ptr())
+            _p(out), _p(out_lo), _p(d_out), out.stride(1), _p(lse), _p(delta), _p(dq), dq.stride(1), _p(dk),
+            dk.stride(1), _p(dv), dv.stride(1), B, H, Sq, Sk, float(scale), _l.stream_ptr())
 
 
 def _strides_bhsd(t):
@@ -554,13 +559,13 @@ class _EncFwdArgs(_ct.Structure):
                 + [("dropout_p", _ct.c_float), ("eps", _ct.c_float), ("seed", _ct.c_uint64),
                    ("x_in", _ct.c_void_p), ("out", _ct.c_void_p), ("y1", _ct.c_void_p), ("y2", _ct.c_void_p * 2)]
                 + [(n, _PP) for n in ("wqkv", "wo", "w1", "w2", "b1", "b2", "g1", "be1", "g2", "be2",
-                                      "xs", "mean1", "rstd1", "xn1", "qkv", "ctx", "lse",
+                                      "xs", "mean1", "rstd1", "xn1", "qkv", "ctx", "lse", "ctx_lo",
                                       "xmid", "mean2", "rstd2", "xn2", "u", "h")])
 
 
 class _EncBwdArgs(_ct.Structure):
     _fields_ = ([("fwd", _ct.POINTER(_EncFwdArgs)), ("gout", _ct.c_void_p), ("dx", _ct.c_void_p)]
-                + [(n, _ct.c_void_p) for n in ("dbranch", "du", "dxn", "dctx", "dqkv")]
+                + [(n, _ct.c_void_p) for n in ("dbranch", "du", "dxn", "dctx", "dqkv", "delta")]
                 + [("gs", _ct.c_void_p * 2)]
                 + [(n, _PP) for n in ("dwqkv", "dwo", "dw1", "db1", "dw2", "db2", "dg1", "dbe1", "dg2", "dbe2")]
                 + [("l_begin", _ct.c_int64), ("l_end", _ct.c_int64)])
@@ -603,6 +608,7 @@ def encoder_stack_fwd(x, weights, params, H, p, seed, need_grad, eps=1e-5):
     xn1 = torch.empty((n, M, D), device=dev, dtype=bf)
     qkv = torch.empty((n, M, 3 * D), device=dev, dtype=bf)
     ctx = torch.empty((n, M, D), device=dev, dtype=bf)
+    ctx_lo = torch.empty((n, M, D), device=dev, dtype=bf) if need_grad else None  # rounding residual of ctx (backward only)
     lse = torch.empty((n, B * H * S), device=dev, dtype=f32)
     xmid = torch.empty((n, M, D), device=dev, dtype=f32)
     xn2 = torch.empty((n, M, D), device=dev, dtype=bf)
@@ -615,7 +621,7 @@ def encoder_stack_fwd(x, weights, params, H, p, seed, need_grad, eps=1e-5):
     a.x_in, a.out = _p(x), _p(out)
     a.y1 = _p(ytmp[0])
     a.y2[0], a.y2[1] = _p(ytmp[1]), _p(ytmp[2])
-    keep = [x, out, xs, stats, xn1, qkv, ctx, lse, xmid, xn2, uh, ytmp, weights, params]
+    keep = [x, out, xs, stats, xn1, qkv, ctx, lse, xmid, xn2, uh, ytmp, weights, params, ctx_lo]
     arrays = {}
     for i, name in enumerate(("wqkv", "wo", "w1", "w2")):
         arrays[name] = _list_ptrs([w[i] for w in weights])
@@ -629,6 +635,8 @@ def encoder_stack_fwd(x, weights, params, H, p, seed, need_grad, eps=1e-5):
     for name, t in (("xn1", xn1), ("qkv", qkv), ("ctx", ctx), ("lse", lse), ("xmid", xmid), ("xn2", xn2),
                     ("u", uh[0]), ("h", uh[1])):
         arrays[name] = _layer_ptrs(t, L, per)
+    if ctx_lo is not None:
+        arrays["ctx_lo"] = _layer_ptrs(ctx_lo, L, per)
     for name, arr in arrays.items():
         setattr(a, name, _ct.cast(arr, _PP))
     keep.append(arrays)
@@ -670,6 +678,7 @@ class EncoderStackBackward:
         du = torch.empty((M, F_), device=dev, dtype=bf)
         dqkv = torch.empty((M, 3 * D), device=dev, dtype=bf)
         gs = torch.empty((2, M, D), device=dev, dtype=f32)
+        delta = torch.empty((B * H * S,), device=dev, dtype=f32)
         shapes = _STACK_GRAD_SHAPES(D, F_)
         self.per_layer = sum(int(torch.Size(shp).numel()) for _, shp in shapes)
         if flat is None:
@@ -688,13 +697,13 @@ class EncoderStackBackward:
         b.fwd = _ct.pointer(st.args)
         b.gout, b.dx = _p(gout), _p(self.dx)
         b.dbranch, b.dxn, b.dctx = _p(tmp_d[0]), _p(tmp_d[1]), _p(tmp_d[2])
-        b.du, b.dqkv = _p(du), _p(dqkv)
+        b.du, b.dqkv, b.delta = _p(du), _p(dqkv), _p(delta)
         b.gs[0], b.gs[1] = _p(gs[0]), _p(gs[1])
         arrays = {name: (_ct.c_void_p * L)(*[_p(t) for t in views]) for name, views in g.items()}
         for name, arr in arrays.items():
             setattr(b, name, _ct.cast(arr, _PP))
         self.args = b
-        self.keep = (gout, tmp_d, du, dqkv, gs, arrays)
+        self.keep = (gout, tmp_d, du, dqkv, gs, delta, arrays)
 
     def run(self, l_begin, l_end):
         self.args.l_begin, self.args.l_end = int(l_begin), int(l_end)
