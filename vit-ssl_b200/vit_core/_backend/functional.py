@@ -179,7 +179,10 @@ def attention_probs(q, k, H):
 # params per block (12): wq wk wv wo | w1 b1 w2 b2 | g1 be1 g2 be2
 # dropout sites per block l: 3l (after out-proj), 3l+1 (after GELU), 3l+2 (after FFN)
 # ----------------------------------------------------------------------------------------
-DP_STACK_CHUNKS = 4  # layer chunks of the stack backward under data parallelism (3 layers each for L = 12)
+import os as _os
+
+# layer chunks of the stack backward under data parallelism (3 layers each for L = 12 at the default 4)
+DP_STACK_CHUNKS = int(_os.environ.get("VITSSL_DP_CHUNKS", "4"))
 
 
 class _EncoderStackFn(torch.autograd.Function):
