@@ -21,6 +21,33 @@ namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// 16-byte shared-memory store with the state space spelled out
+__device__ __forceinline__ void sts128_(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// One thread's 32 consecutive fp32 values (raw bits) of row `lane` -> a 32 x 32 bf16 staging block
+// (64-byte rows in the TMA SWIZZLE_64B pattern) that a TMA store then writes as full lines; per-thread
+// 16-byte global stores would touch 32 different lines per instruction. LO = false: bf16(x * mul);
+// LO = true: the rounding residual bf16(x * mul - bf16(x * mul)).
+template <bool LO>
+__device__ __forceinline__ void stage_block32(uint32_t dst, int lane, const uint32_t (&v)[32], float mul) {
+  const uint32_t base = dst + lane * 64;
+  const int sw = (lane >> 1) & 3;
+  const f32x2 m2 = pk2(mul, mul);
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x0, x1;
+      upk2(fmul2(pk2(__uint_as_float(v[8 * q4 + 2 * e]), __uint_as_float(v[8 * q4 + 2 * e + 1])), m2), x0, x1);
+      uint32_t hi = pack_bf16(x0, x1);
+      w[e] = LO ? pack_bf16(x0 - bf16_lo(hi), x1 - bf16_hi(hi)) : hi;
+    }
+    sts128_(base + ((q4 ^ sw) << 4), w[0], w[1], w[2], w[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
@@ -30,13 +57,15 @@ struct AttnFwdParams {
   float* lse;                         // [B, H, Sq] log-sum-exp of the scaled scores
   int B, H, Sq, Sk, kv_rows;          // kv_rows = round_up(Sk, 16) <= 256
   float scale;
+  int staged;                         // 1: context leaves through shared-memory staging + TMA stores
 };
 
 constexpr int FWD_THREADS = 192;  // warps 0-3 softmax (TMEM lane quadrant = warp), 4 = TMA, 5 = MMA
 constexpr int FWD_SMEM_Q = 0;               // 16 KB: 128 query rows x 128 B
 constexpr int FWD_SMEM_K = 16384;           // 32 KB: up to 256 key rows
 constexpr int FWD_SMEM_V = 16384 + 32768;   // 32 KB
-constexpr int FWD_SMEM_BAR = 16384 + 65536;
+constexpr int FWD_SMEM_STG = 16384 + 65536;  // 16 KB: two 32 x 32 bf16 staging blocks (2 KB each) per softmax warp
+constexpr int FWD_SMEM_BAR = FWD_SMEM_STG + 16384;
 constexpr int FWD_SMEM_BYTES = FWD_SMEM_BAR + 128 + 1024;
 constexpr uint32_t FWD_COL_O = 128;  // O accumulator columns [128,192): inside S, past the packed P
 
@@ -49,7 +78,8 @@ constexpr uint32_t FWD_COL_O = 128;  // O accumulator columns [128,192): inside 
 // (attention.py:20-23 materialises it three times).
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                const __grid_constant__ CUtensorMap tmap_olo, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -73,6 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+      tma_prefetch_desc(&tmap_o); tma_prefetch_desc(&tmap_olo);
       mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1);
       mbar_init(bar_p, 4); mbar_init(bar_o, 1); mbar_init(bar_oread, 4);
       fence_barrier_init();
@@ -231,7 +262,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_oread);  // O is in registers: the next item's S MMA may overwrite TMEM
-        if (qrow < p.Sq) {
+        if (p.staged) {
+          // 32 rows x 64 columns per warp as two 32 x 32 blocks -> swizzled staging -> TMA stores (full
+          // 64-byte row segments, clipped at Sq); the rounding residual reuses the blocks afterwards
+          const uint32_t stg = smem_u32(smem + FWD_SMEM_STG + warp * 4096);
+          const int row0 = qt * 128 + warp * 32;
+          if (lane == 0) tma_store_wait_read<0>();  // the previous item's stores have drained the blocks
+          __syncwarp();
+          stage_block32<false>(stg, lane, r0, inv);
+          stage_block32<false>(stg + 2048, lane, r1, inv);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_o, smem + FWD_SMEM_STG + warp * 4096, h * 64, row0, b);
+            tma_store_3d(&tmap_o, smem + FWD_SMEM_STG + warp * 4096 + 2048, h * 64 + 32, row0, b);
+            tma_store_commit();
+          }
+          if (p.out_lo) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            stage_block32<true>(stg, lane, r0, inv);
+            stage_block32<true>(stg + 2048, lane, r1, inv);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmap_olo, smem + FWD_SMEM_STG + warp * 4096, h * 64, row0, b);
+              tma_store_3d(&tmap_olo, smem + FWD_SMEM_STG + warp * 4096 + 2048, h * 64 + 32, row0, b);
+              tma_store_commit();
+            }
+          }
+          if (qrow < p.Sq && p.lse)
+            p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qrow] = mx * p.scale + __logf(sum);
+        } else if (qrow < p.Sq) {
           const long long ooff = (static_cast<long long>(b) * p.Sq + qrow) * p.ldo + h * 64;
           __nv_bfloat16* op = p.out + ooff;
           // 8 context values -> 16 bytes of bf16, and (training) 16 bytes of their bf16 rounding
@@ -262,6 +324,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   }
+  if (warp < 4 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
@@ -921,6 +984,21 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
   if ((rc = make_head_map(&mq, q, p.B, p.Sq, p.H, ldq, 128))) return rc;
   if ((rc = make_head_map(&mk, k, p.B, p.Sk, p.H, ldk, p.kv_rows))) return rc;
   if ((rc = make_head_map(&mv, v, p.B, p.Sk, p.H, ldv, p.kv_rows))) return rc;
+  // the context (and its rounding residual) leave through 32 x 32 staging blocks + TMA stores when the
+  // output rows are TMA-addressable (VITSSL_ATTN_FWD_STAGED=0 forces per-thread stores)
+  static const int staged_env = getenv("VITSSL_ATTN_FWD_STAGED") ? atoi(getenv("VITSSL_ATTN_FWD_STAGED")) : 1;
+  CUtensorMap mo, molo;
+  memset(&mo, 0, sizeof(mo));
+  memset(&molo, 0, sizeof(molo));
+  p.staged = staged_env != 0 ? 1 : 0;
+  if (p.staged) {
+    auto out_map = [&](CUtensorMap* m, void* base) {
+      return make_tmap_bf16_3d_sw(m, base, (uint64_t)p.H * 64, (uint64_t)p.Sq, (uint64_t)p.B, (uint64_t)ldo * 2,
+                                  (uint64_t)p.Sq * ldo * 2, 32, 32, 1, 64);
+    };
+    if ((rc = out_map(&mo, out))) return rc;
+    if ((rc = out_map(&molo, out_lo ? out_lo : out))) return rc;
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
@@ -930,7 +1008,7 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
   const long long items = (long long)B * H * ((Sq + 127) / 128);
   const long long slots = 2ll * num_sms();  // persistent: two CTAs per SM
   const unsigned grid = (unsigned)(items < slots ? items : slots);
-  cudaError_t lerr = launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, p);
+  cudaError_t lerr = launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, mo, molo, p);
   if (lerr != cudaSuccess) { set_error("attention_fwd: launch failed: %s", cudaGetErrorString(lerr)); return VITSSL_ERR_CUDA; }
   return check_launch("attention_fwd");
 }
