@@ -677,20 +677,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const float dl = i ? delta1 : delta0, nl = i ? nlse1 : nlse0;
         const f32x2 sl2v = pk2(sl2, sl2), nlv = pk2(nl, nl), ndlv = pk2(-dl, -dl);
         const int keyb = j * 128 + cq * 32;  // this thread's first key
+        // a warp whose 32 query rows all lie past Sq (S = 196: the last quadrant of the second query
+        // tile; S = 37: three of four quadrants) has nothing to compute: its P / dS rows are zero. It
+        // keeps every barrier hand-off but skips the TMEM reads and the exp math (key_lim = 0).
+        const int key_lim = (i * 128 + (warp & 3) * 32 < p.Sq) ? p.Sk : 0;
         // 8 keys: P = 2^(S * scale * log2e - lse * log2e), dS = P * (dP - delta), one 16-byte store each
         auto sub_chunk = [&](const uint32_t (&sv)[8], const uint32_t (&dp)[8], int c) {
           const int key0 = keyb + c * 8;
           uint32_t pp[4], dd[4];
-          if (key0 < p.Sk) {
-            const bool full = key0 + 8 <= p.Sk;
+          if (key0 < key_lim) {
+            const bool full = key0 + 8 <= key_lim;
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
               float a0, a1;
               upk2(ffma2(pk2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2v, nlv), a0, a1);
               float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
               if (!full) {
-                p0 = (key0 + e < p.Sk) ? p0 : 0.f;
-                p1 = (key0 + e + 1 < p.Sk) ? p1 : 0.f;
+                p0 = (key0 + e < key_lim) ? p0 : 0.f;
+                p1 = (key0 + e + 1 < key_lim) ? p1 : 0.f;
               }
               pp[e >> 1] = pack_bf16(p0, p1);
               float d0, d1;
@@ -721,7 +725,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             __syncwarp();
-            if (keyb + c * 8 < p.Sk) {
+            if (keyb + c * 8 < key_lim) {
               tmem_ld_32x8(ts + c * 8, sv);
               tmem_ld_32x8(td + c * 8, dp);
               tmem_ld_wait();
@@ -734,10 +738,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           // warp (next iteration's S / dP) with half of this iteration's exp math still to do
           uint32_t sv2[8], dp2[8], sv3[8], dp3[8];
           __syncwarp();
-          if (keyb + 16 < p.Sk) {
+          if (keyb + 16 < key_lim) {
             tmem_ld_32x8(ts + 16, sv2);
             tmem_ld_32x8(td + 16, dp2);
-            if (keyb + 24 < p.Sk) {
+            if (keyb + 24 < key_lim) {
               tmem_ld_32x8(ts + 24, sv3);
               tmem_ld_32x8(td + 24, dp3);
             }
