@@ -428,12 +428,15 @@ def run_gpu_arm(args):
     value = world * B * args.steps / (ms_total / 1e3)
     final_loss = float(loss.detach())
 
-    # host time to ISSUE a step (no synchronisation inside): the margin by which the step is GPU-bound
-    barrier()
-    th0 = time.perf_counter()
-    for i in range(5):
+    # host time to ISSUE one step into an idle stream (no synchronisation inside, launch queue empty,
+    # so the host never waits for the device): the margin by which the step is GPU-bound
+    issue = []
+    for i in range(3):
+        barrier()
+        th0 = time.perf_counter()
         step(dev_in[i % n_host])
-    host_issue_ms = (time.perf_counter() - th0) / 5 * 1e3
+        issue.append((time.perf_counter() - th0) * 1e3)
+    host_issue_ms = statistics.median(issue)
     barrier()
 
     # ---- timed region 2: end to end (pinned host -> device each step, loss read back each step) ----

@@ -128,7 +128,7 @@ def test_committed_launch_list_reproduces_the_traffic_table(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = tmp_path / "traffic.json"
     subprocess.run([sys.executable, os.path.join(root, "scripts", "summarize_launches.py"),
-                    os.path.join(root, "profiles", "r1_launches.csv"), str(out)], check=True, capture_output=True)
+                    os.path.join(root, "profiles", "r2_launches.csv"), str(out)], check=True, capture_output=True)
     got, want = json.load(open(out)), json.load(open(os.path.join(root, "profiles", "traffic.json")))
     for fam in ("gemm_tcgen05_kernel", "ln_kernel", "attn_bwd_kernel", "attn_fwd_kernel"):
         assert got[fam] == want[fam], fam
