@@ -264,8 +264,8 @@ class _EncoderStackFn(torch.autograd.Function):
             # starts its all-reduce on the communication stream while the next chunk computes
             sync = dp.sync_for(ctx.params) if all(ctx.needs_input_grad[2:]) else None
             run = ops.EncoderStackBackward(st, g)
-            n_chunks = min(L, DP_STACK_CHUNKS) if sync is not None else 1
-            bounds = [round(i * L / n_chunks) for i in range(n_chunks + 1)]
+            bounds = dp_chunk_bounds(L, DP_STACK_CHUNKS) if sync is not None else [0, L]
+            n_chunks = len(bounds) - 1
             for c in reversed(range(n_chunks)):
                 run.run(bounds[c], bounds[c + 1])
                 if sync is not None:
@@ -369,8 +369,8 @@ class _EncoderStackMultiFn(torch.autograd.Function):
             flat = r.flat
             runs.append(r)
         sync = dp.sync_for(ctx.params) if all(ctx.needs_input_grad[2 + n_in:]) else None
-        n_chunks = min(L, DP_STACK_CHUNKS) if sync is not None else 1
-        bounds = [round(i * L / n_chunks) for i in range(n_chunks + 1)]
+        bounds = dp_chunk_bounds(L, DP_STACK_CHUNKS) if sync is not None else [0, L]
+        n_chunks = len(bounds) - 1
         for c in reversed(range(n_chunks)):
             for r in runs:
                 r.run(bounds[c], bounds[c + 1])
@@ -421,6 +421,17 @@ def encoder_stack(blocks: Sequence, x: torch.Tensor, return_attn: bool = False):
     if return_attn:
         return out[0], out[1]
     return out, None
+
+
+def dp_chunk_bounds(L: int, n_chunks: int):
+    """Layer boundaries of the data-parallel stack backward (processed from the top chunk down). The
+    chunk that runs LAST — the lowest layers — is a single layer: its all-reduce is the one nothing
+    is left to overlap with, so it should be the smallest (7 MB instead of 22 MB for ViT-S/16)."""
+    n_chunks = max(1, min(int(n_chunks), L))
+    if n_chunks < 3 or L < n_chunks + 1:
+        return [round(i * L / n_chunks) for i in range(n_chunks + 1)]
+    rest = [1 + round(i * (L - 1) / (n_chunks - 1)) for i in range(n_chunks)]
+    return [0] + rest
 
 
 def encoder_stack_multi(blocks: Sequence, xs: Sequence[torch.Tensor]):
