@@ -359,7 +359,7 @@ constexpr int BWD_THREADS = 32 * (BWD_MATH_WARPS + 2);
 constexpr int BWD_TILE = 16384;  // one 128-row x 64-column bf16 tile (128-byte swizzled rows)
 constexpr int BWD_SMEM_Q = 0 * BWD_TILE;    // 2 slots each: Q, dO, O (query tiles), K, V (key tiles)
 constexpr int BWD_SMEM_DO = 2 * BWD_TILE;
-constexpr int BWD_SMEM_O = 4 * BWD_TILE;
+constexpr int BWD_SMEM_O = 4 * BWD_TILE;    // (no O tiles any more: delta has its own pass) staging of the accumulator drains
 constexpr int BWD_SMEM_K = 6 * BWD_TILE;
 constexpr int BWD_SMEM_VV = 8 * BWD_TILE;
 constexpr int BWD_SMEM_P = 10 * BWD_TILE;   // P and dS of the current iteration: 2 key blocks x 16 KB each
@@ -581,10 +581,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // warps 8-15 dK; 32 of the 64 columns each), dQ when the item is complete (thread group cq
     // takes columns (cq & 1) * 32 .. +32 of query tile cq >> 1). The drains of iteration g run
     // inside iteration g+1, after its first exp math and before its P / dS stores, so waiting for
-    // the MMAs of iteration g costs nothing; at that point the P / dS region is idle, so each warp
-    // stages its 32 x 32 bf16 block there (64-byte swizzle) and hands it to a TMA store, which
-    // clips at the sequence end. (Per-thread 16-byte global stores hit 32 different lines per
-    // instruction and took ~2500 cycles per drain in the LSU.)
+    // the MMAs of iteration g costs nothing; each warp stages its 32 x 32 bf16 block (64-byte
+    // swizzle) and hands it to a TMA store, which clips at the sequence end. (Per-thread 16-byte
+    // global stores hit 32 different lines per instruction and took ~2500 cycles per drain in the LSU.)
     auto stage32 = [&](uint32_t dst, const uint32_t (&v)[32], float mul) {
       const uint32_t base = dst + lane * 64;
       const int sw = (lane >> 1) & 3;
@@ -601,23 +600,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         sts128(base + ((q4 ^ sw) << 4), w[0], w[1], w[2], w[3]);
       }
     };
+    // Staging lives in the two tile slots that held the O tiles before delta moved to its own pass
+    // (16 warps x 2 KB): the P / dS region is never touched, so a drain needs neither a wait for the
+    // TMA engine to finish reading nor a CTA-wide barrier before P / dS of the current iteration are
+    // stored (per-iteration trace of the former form: ~2 500-3 000 of ~6 000 cycles in the two
+    // draining iterations of an item). A warp only waits for ITS previous store before it restages.
     auto drain = [&](int item, int j, bool item_done) {
       const int h = item % p.H, b = item / p.H;
       const int sel = cq >> 1, cc = cq & 1;
-      uint8_t* stg = smem + BWD_SMEM_P + warp * 4096;
-      {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32(lane_addr + (sel == 0 ? COL_DV : COL_DK) + cc * 32, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_addr(sbar + 8 * 12);  // bar_dkv_free: accumulators are in registers
-        stage32(smem_u32(stg), v, sel == 0 ? 1.0f : p.scale);
-      }
+      uint8_t* stg = smem + BWD_SMEM_O + warp * 2048;
+      const int row0 = (warp & 3) * 32, col0 = h * 64 + cc * 32;
       const bool dq_mine = item_done && sel < nq;
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld_32x32(lane_addr + (sel == 0 ? COL_DV : COL_DK) + cc * 32, v);
+      if (lane == 0) tma_store_wait_read<0>();  // this warp's block: its previous store has read it (long ago)
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_addr(sbar + 8 * 12);  // bar_dkv_free: accumulators are in registers
+      stage32(smem_u32(stg), v, sel == 0 ? 1.0f : p.scale);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(sel == 0 ? &tmap_dv : &tmap_dk, stg, col0, j * 128 + row0, b);
+        tma_store_commit();
+      }
       if (item_done) {
-        uint32_t v[32];
         __syncwarp();
         if (dq_mine) {
           tmem_ld_32x32(lane_addr + COL_DQ + sel * 64 + cc * 32, v);
@@ -626,18 +635,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_addr(sbar + 8 * 13);  // bar_dq_free
-        if (dq_mine) stage32(smem_u32(stg) + 2048, v, p.scale);
+        if (dq_mine) {
+          if (lane == 0) tma_store_wait_read<0>();  // the dV / dK store above has read the block
+          __syncwarp();
+          stage32(smem_u32(stg), v, p.scale);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_dq, stg, col0, sel * 128 + row0, b);
+            tma_store_commit();
+          }
+        }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const int row0 = (warp & 3) * 32, col0 = h * 64 + cc * 32;
-        tma_store_3d(sel == 0 ? &tmap_dv : &tmap_dk, stg, col0, j * 128 + row0, b);
-        if (dq_mine) tma_store_3d(&tmap_dq, stg + 2048, col0, sel * 128 + row0, b);
-        tma_store_commit();
-        tma_store_wait_read<0>();  // the staging block is about to be overwritten with P / dS
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * BWD_MATH_WARPS) : "memory");  // ... by any math warp
     };
 
     // -lse * log2(e) and delta = rowsum(O * dO) of this thread's two query rows ([B, H, Sq] = [item, Sq]
@@ -994,7 +1003,9 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
   CUtensorMap mo, molo;
   memset(&mo, 0, sizeof(mo));
   memset(&molo, 0, sizeof(molo));
-  p.staged = staged_env != 0 ? 1 : 0;
+  // short sequences (S = 37: DINO local crops, cfg 1) keep per-thread stores: most of a 32-row block
+  // would be clipped and the staging round trip costs more than it saves (58 vs 54 us at S = 37)
+  p.staged = (staged_env == 2 || (staged_env == 1 && Sq > 64)) ? 1 : 0;
   if (p.staged) {
     auto out_map = [&](CUtensorMap* m, void* base) {
       return make_tmap_bf16_3d_sw(m, base, (uint64_t)p.H * 64, (uint64_t)p.Sq, (uint64_t)p.B, (uint64_t)ldo * 2,
