@@ -328,6 +328,21 @@ int vitssl_dino_loss_bwd(const void* teacher, const void* student, const float* 
                          void* dstudent, int64_t G, int64_t V, int64_t B, int64_t K,
                          float teacher_temp, float student_temp, vitssl_stream_t stream);
 
+/* ---- evaluation path ---------------------------------------------------------- */
+/* out[b,:] = mean_s x[b,s,:] — the token mean-pool of SimMIMViT.inference_forward
+ * (ssl/simmim/model.py:91-93). fp32 [B,S,D] dense, D % 4 == 0. */
+int vitssl_mean_tokens_f32(const float* x, float* out, int64_t B, int64_t S, int64_t D,
+                           vitssl_stream_t stream);
+/* Cosine k-nearest-neighbour classification of fp32 feature rows — what the reference's evaluator
+ * does with scikit-learn on the CPU (evaluators/unsupervised_evaluator.py:38-66:
+ * KNeighborsClassifier(n_neighbors=num_classes, metric="cosine").fit(train).predict(val)): rows are
+ * L2-normalised, the k most similar training rows are taken (smaller index first on exact ties) and
+ * vote uniformly (smallest label on ties). Caller-provided workspaces: val_n [Nv,D], train_n [Nt,D],
+ * sims [Nv,Nt] fp32 (consumed). pred int32 [Nv]; neighbors int32 [Nv,k] nullable. */
+int vitssl_knn_cosine(const float* val, const float* train, const int32_t* train_labels, float* val_n,
+                      float* train_n, float* sims, int32_t* pred, int32_t* neighbors, int64_t Nv,
+                      int64_t Nt, int64_t D, int64_t k, int64_t num_classes, vitssl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -335,3 +335,65 @@ def test_dino_loss_general_shapes(tshape, sshape):
     assert rel_l2(s.grad, sb.grad) <= 1e-2
     with pytest.raises(ValueError):
         DINOLoss(0.05, 0.1)(t.cuda()[..., :8], s, c.cuda())
+
+
+# ------------------------------------------------------------------------------------------
+# view packing: a list of equally-shaped crops == their concatenation, bit for bit
+# ------------------------------------------------------------------------------------------
+def test_view_lists_are_embedded_like_their_concatenation():
+    from oracle.cases import build_dino_case
+    from vit_core import DynamicPatchEmbedding
+    from vit_core.ssl.dino import DINOViT
+    torch.manual_seed(0)
+    m = DynamicPatchEmbedding((3, 32, 32), 64, 8).cuda()
+    views = [torch.rand(3, 3, 32, 32, device="cuda") for _ in range(3)]
+    a = m(views)
+    b = m(torch.cat(views))
+    assert a.shape == (9, 17, 64) and torch.equal(a, b)
+    a.sum().backward()
+    g1 = m.proj.weight.grad.clone()
+    m.zero_grad()
+    m(torch.cat(views)).sum().backward()
+    assert torch.equal(g1, m.proj.weight.grad)
+    u8 = [torch.randint(0, 256, (2, 3, 16, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    assert torch.equal(m(u8), m(torch.cat(u8)))
+    with pytest.raises(ValueError):
+        m([views[0], views[1][:, :, :16, :16]])
+    # the whole DINO forward: list-of-views path (no torch.cat of images) == reference-shaped call
+    cfg, dm, dviews, B = build_dino_case(DINOViT)
+    dm.cuda().eval()
+    with torch.no_grad():
+        t1, s1 = dm([v.cuda() for v in dviews], 2)
+        c1 = dm.center.clone()
+        g = torch.cat([v.cuda() for v in dviews[:2]])
+        t2 = dm.teacher_head(dm.teacher_backbone(g))
+    assert torch.equal(t1, t2) and t1.shape == (2 * B, 512)
+
+
+# ------------------------------------------------------------------------------------------
+# evaluation path: token mean-pool kernel and GPU cosine k-NN vs scikit-learn
+# ------------------------------------------------------------------------------------------
+def test_mean_tokens_kernel_and_simmim_inference():
+    from vit_core._backend import ops
+    x = torch.randn(7, 37, 192, device="cuda")
+    assert (ops.mean_tokens(x) - x.mean(dim=1)).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("Nt,Nv,D,classes", [(500, 300, 64, 10), (1203, 777, 384, 10), (64, 33, 20, 3)])
+def test_gpu_knn_matches_sklearn_cosine_knn(Nt, Nv, D, classes):
+    sk = pytest.importorskip("sklearn.neighbors")
+    from vit_core.evaluation import knn_predict, run_knn_evaluation
+    g = torch.Generator().manual_seed(Nt + Nv)
+    centers = torch.randn(classes, D, generator=g)
+    yt = torch.randint(0, classes, (Nt,), generator=g)
+    yv = torch.randint(0, classes, (Nv,), generator=g)
+    xt = centers[yt] + 1.5 * torch.randn(Nt, D, generator=g)
+    xv = centers[yv] + 1.5 * torch.randn(Nv, D, generator=g)
+    knn = sk.KNeighborsClassifier(n_neighbors=classes, metric="cosine")     # evaluators/unsupervised_evaluator.py:52
+    knn.fit(xt.numpy(), yt.numpy())
+    want = torch.from_numpy(knn.predict(xv.numpy()))
+    got = knn_predict(xt.cuda(), yt.cuda(), xv.cuda(), classes)
+    agree = (got.cpu() == want).float().mean().item()
+    assert agree >= 0.995, agree          # identical up to float-rounding of near-tied distances
+    res = run_knn_evaluation(xt, yt, xv, yv, classes)
+    assert abs(res["accuracy"] - (want == yv).float().mean().item()) <= 0.01 and res["num_neighbors"] == classes

@@ -690,11 +690,22 @@ class _EmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, meta, weight, bias, cls, pos, mask_token):
         p = meta.patch
-        img = _as_image(img)
-        B, C, Hh, Ww = img.shape
-        N = (Hh // p) * (Ww // p)
         D = weight.shape[0]
-        patches = ops.im2col_bf16(img, p)
+        if meta.views is not None:
+            # several equally-shaped image batches (DINO's crops of one resolution, model.py:114-115):
+            # each is unfolded straight into its slice of ONE patch matrix - no torch.cat of the images
+            views = [_as_image(v) for v in meta.views]
+            Bv, C, Hh, Ww = views[0].shape
+            N = (Hh // p) * (Ww // p)
+            B = Bv * len(views)
+            patches = torch.empty((B * N, C * p * p), device=views[0].device, dtype=torch.bfloat16)
+            for i, v in enumerate(views):
+                ops.im2col_bf16(v, p, out=patches[i * Bv * N:(i + 1) * Bv * N])
+        else:
+            img = _as_image(img)
+            B, C, Hh, Ww = img.shape
+            N = (Hh // p) * (Ww // p)
+            patches = ops.im2col_bf16(img, p)
         proj = ops.gemm(patches, meta.w_bf16, epilogue=EPI_BIAS, bias=bias)
         cls_v = cls.reshape(-1).contiguous() if cls is not None else None
         pos_v = pos.reshape(-1, D).contiguous()
@@ -732,6 +743,14 @@ def embed_patches(img, owner, weight, bias, cls, pos, patch, mask_u8=None, mask_
     Shape errors surface here as ValueError, like the reference's broadcast failure in
     `x += positional_embedding` (patch_embedding.py:63,95; ssl/simmim/model.py:49) — the kernels
     index `pos` by token and would otherwise read out of bounds."""
+    views = None
+    if isinstance(img, (list, tuple)):
+        views = list(img)
+        if not views or any(v.dim() != 4 or v.shape != views[0].shape or v.dtype != views[0].dtype for v in views):
+            raise ValueError("a list of views must hold equally-shaped [B,C,H,W] batches of one dtype")
+        img = views[0]
+        if len(views) == 1:
+            views = None
     if img.dim() != 4:
         raise ValueError(f"expected images [B,C,H,W], got {tuple(img.shape)}")
     B, C, Hh, Ww = img.shape
@@ -749,7 +768,7 @@ def embed_patches(img, owner, weight, bias, cls, pos, patch, mask_u8=None, mask_
     if mask_token is not None and mask_token.numel() != D:
         raise ValueError(f"mask_token {tuple(mask_token.shape)} does not have {D} features")
     (w_bf16,) = bf16_shadows([(owner, "wproj", [weight])])
-    meta = SimpleNamespace(patch=int(patch), w_bf16=w_bf16, mask_u8=mask_u8)
+    meta = SimpleNamespace(patch=int(patch), w_bf16=w_bf16, mask_u8=mask_u8, views=views)
     return _EmbedFn.apply(img, meta, weight, bias, cls, pos, mask_token)
 
 

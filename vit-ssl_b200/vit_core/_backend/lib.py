@@ -68,6 +68,8 @@ SIGNATURES["vitssl_l1_loss_bwd"] = "pppl" + "s"
 SIGNATURES["vitssl_adamw_step"] = "ppppppp" + "i" + "fffff" + "pp" + "s"
 SIGNATURES["vitssl_profile_read"] = "lplpp"
 SIGNATURES["vitssl_multi_ema_shadow"] = "ppppifs"
+SIGNATURES["vitssl_mean_tokens_f32"] = "pp" + "lll" + "s"
+SIGNATURES["vitssl_knn_cosine"] = "pppppppp" + "lllll" + "s"
 
 _lib = None
 

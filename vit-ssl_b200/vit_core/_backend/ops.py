@@ -325,15 +325,49 @@ def colsum_bf16(x):
     return out
 
 
-def im2col_bf16(img, p):
-    """img: fp32 [B,C,H,W], or raw uint8 image bytes (value = byte / 255, torchvision ToTensor)."""
+def im2col_bf16(img, p, out=None):
+    """img: fp32 [B,C,H,W], or raw uint8 image bytes (value = byte / 255, torchvision ToTensor).
+    `out`: optional contiguous bf16 [B*N, C*p*p] destination (a slice of a larger patch buffer: several
+    views are packed into one GEMM operand without a concatenated copy of the images)."""
     _l.ensure_device()
     assert img.dtype in (torch.float32, torch.uint8) and img.is_contiguous() and img.dim() == 4
     B, C, H, W = img.shape
-    out = torch.empty((B * (H // p) * (W // p), C * p * p), device=img.device, dtype=torch.bfloat16)
+    rows, cols = B * (H // p) * (W // p), C * p * p
+    if out is None:
+        out = torch.empty((rows, cols), device=img.device, dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and out.shape == (rows, cols) and out.is_contiguous()
     name = "vitssl_im2col_bf16" if img.dtype == torch.float32 else "vitssl_im2col_u8_bf16"
     _l.call(name, _p(img), _p(out), B, C, H, W, p, _l.stream_ptr())
     return out
+
+
+def mean_tokens(x):
+    """fp32 [B,S,D] -> [B,D] mean over tokens (ssl/simmim/model.py:91-93)."""
+    _l.ensure_device()
+    assert x.dtype == torch.float32 and x.dim() == 3 and x.is_contiguous()
+    B, S, D = x.shape
+    out = torch.empty((B, D), device=x.device, dtype=torch.float32)
+    _l.call("vitssl_mean_tokens_f32", _p(x), _p(out), B, S, D, _l.stream_ptr())
+    return out
+
+
+def knn_cosine(val, train, train_labels, k, num_classes, want_neighbors=False):
+    """Cosine k-NN vote on the GPU; val [Nv,D], train [Nt,D] fp32, train_labels int [Nt] in [0, num_classes).
+    Returns (pred int32 [Nv], neighbors int32 [Nv,k] | None)."""
+    _l.ensure_device()
+    val = val.float().contiguous()
+    train = train.float().contiguous()
+    lab = train_labels.to(device=val.device, dtype=torch.int32).contiguous()
+    Nv, D = val.shape
+    Nt = train.shape[0]
+    assert train.shape[1] == D and lab.numel() == Nt
+    val_n, train_n = torch.empty_like(val), torch.empty_like(train)
+    sims = torch.empty((Nv, Nt), device=val.device, dtype=torch.float32)
+    pred = torch.empty((Nv,), device=val.device, dtype=torch.int32)
+    nbr = torch.empty((Nv, k), device=val.device, dtype=torch.int32) if want_neighbors else None
+    _l.call("vitssl_knn_cosine", _p(val), _p(train), _p(lab), _p(val_n), _p(train_n), _p(sims), _p(pred), _p(nbr),
+            Nv, Nt, D, int(k), int(num_classes), _l.stream_ptr())
+    return pred, nbr
 
 
 def gather_patches_f32(img, rows_idx, p):

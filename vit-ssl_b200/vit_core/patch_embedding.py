@@ -42,7 +42,9 @@ class DynamicPatchEmbedding(nn.Module):
 
     @eager
     def forward(self, x):
-        _, _, height, width = x.shape
+        """x: [B,C,H,W] images, or a list of equally-shaped batches (crops of one resolution), which
+        are embedded as if concatenated along the batch — without materialising the concatenation."""
+        _, _, height, width = (x[0] if isinstance(x, (list, tuple)) else x).shape
         if height % self.patch_size != 0 or width % self.patch_size != 0:
             raise ValueError(
                 f"Input image dimensions ({height}x{width}) must be divisible by patch size ({self.patch_size})."

@@ -91,10 +91,15 @@ class DINOViT(nn.Module):
     @eager
     def forward(self, multi_crop_views: List[torch.Tensor], num_global_views: int):
         dp.maybe_attach(self)
-        global_crops = torch.cat(multi_crop_views[:num_global_views], dim=0)
+        # view packing: the crops of one resolution go to the patch kernels as a list and
+        # are unfolded into one patch matrix; the reference concatenates the images first (model.py:114-115)
+        views = list(multi_crop_views)
+        same = lambda vs: all(v.shape == vs[0].shape and v.dtype == vs[0].dtype for v in vs)
+        global_views, local_views = views[:num_global_views], views[num_global_views:]
+        global_crops = global_views if same(global_views) else torch.cat(global_views, dim=0)
         crops = [global_crops]
-        if len(multi_crop_views) > num_global_views:
-            crops.append(torch.cat(multi_crop_views[num_global_views:], dim=0))
+        if local_views:
+            crops.append(local_views if same(local_views) else torch.cat(local_views, dim=0))
         # one backbone node and one head call for all views: rows stay view-major (globals first),
         # as in model.py:117-119
         student_output = self.student_head(self.student_backbone.forward_views(crops))

@@ -100,4 +100,4 @@ class SimMIMViT(nn.Module):
         tokens = Fb.embed_patches(x, self, self.projection.weight, self.projection.bias, None,
                                   self.positional_embedding, self.patch_size)
         tokens, _ = Fb.encoder_stack(self.encoder_blocks, tokens)
-        return tokens if return_patch_features else tokens.mean(dim=1)
+        return tokens if return_patch_features else ops.mean_tokens(tokens.contiguous())
