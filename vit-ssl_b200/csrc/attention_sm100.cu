@@ -76,6 +76,7 @@ constexpr uint32_t FWD_COL_O = 128;  // O accumulator columns [128,192): inside 
 //              back over S in TMEM as packed bf16 (tcgen05.st), then O / rowsum -> global.
 // Nothing of the S x S probability matrix ever reaches shared or global memory
 // (attention.py:20-23 materialises it three times).
+template <bool STAGED>  // context leaves through staging + TMA stores (S > 64) or per-thread stores
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
@@ -262,7 +263,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_oread);  // O is in registers: the next item's S MMA may overwrite TMEM
-        if (p.staged) {
+        if constexpr (STAGED) {
           // 32 rows x 64 columns per warp as two 32 x 32 blocks -> swizzled staging -> TMA stores (full
           // 64-byte row segments, clipped at Sq); the rounding residual reuses the blocks afterwards
           const uint32_t stg = smem_u32(smem + FWD_SMEM_STG + warp * 4096);
@@ -324,7 +325,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   }
-  if (warp < 4 && lane == 0) tma_store_wait_all();
+  if constexpr (STAGED) {
+    if (warp < 4 && lane == 0) tma_store_wait_all();
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
@@ -1016,14 +1019,18 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
+    cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
     if (err != cudaSuccess) { set_error("attention_fwd: smem attribute: %s", cudaGetErrorString(err)); return VITSSL_ERR_CUDA; }
     configured = true;
   }
   const long long items = (long long)B * H * ((Sq + 127) / 128);
   const long long slots = 2ll * num_sms();  // persistent: two CTAs per SM
   const unsigned grid = (unsigned)(items < slots ? items : slots);
-  cudaError_t lerr = launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, mo, molo, p);
+  cudaError_t lerr = p.staged
+      ? launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, mo, molo, p)
+      : launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, mo, molo, p);
   if (lerr != cudaSuccess) { set_error("attention_fwd: launch failed: %s", cudaGetErrorString(lerr)); return VITSSL_ERR_CUDA; }
   return check_launch("attention_fwd");
 }
