@@ -694,9 +694,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // keeps every barrier hand-off but skips the TMEM reads and the exp math (key_lim = 0).
         const int key_lim = (i * 128 + (warp & 3) * 32 < p.Sq) ? p.Sk : 0;
         // 8 keys: P = 2^(S * scale * log2e - lse * log2e), dS = P * (dP - delta), one 16-byte store each
-        auto sub_chunk = [&](const uint32_t (&sv)[8], const uint32_t (&dp)[8], int c) {
+        auto chunk_math = [&](const uint32_t (&sv)[8], const uint32_t (&dp)[8], int c, uint32_t (&pp)[4], uint32_t (&dd)[4]) {
           const int key0 = keyb + c * 8;
-          uint32_t pp[4], dd[4];
           if (key0 < key_lim) {
             const bool full = key0 + 8 <= key_lim;
 #pragma unroll
@@ -717,38 +716,48 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) pp[e] = dd[e] = 0u;
           }
-          if (c == 0 && g > 0) {
-            // the math above overlapped the previous iteration's dV / dK / dQ MMAs; the stores need
-            // their P / dS operands consumed, and that iteration's finished accumulators are drained
-            if (threadIdx.x == 0) TRACE(16 * g + 10);
-            mbar_wait_parked_addr(sbar + 8 * 11, (g - 1) & 1);  // bar_pds_free
-            if (threadIdx.x == 0) TRACE(16 * g + 11);
-            tc_fence_after();
-            if (it == 0) drain(item - static_cast<int>(gridDim.x), nk - 1, true);
-            else if (i == 0) drain(item, j - 1, false);
-          }
+        };
+        auto chunk_store = [&](int c, const uint32_t (&pp)[4], const uint32_t (&dd)[4]) {
           const int sw = (((cq & 1) * 4 + c) ^ (r & 7)) << 4;
           sts128(sP + sw, pp[0], pp[1], pp[2], pp[3]);
           sts128(sP + (BWD_SMEM_DS - BWD_SMEM_P) + sw, dd[0], dd[1], dd[2], dd[3]);
         };
         const uint32_t ts = lane_addr + COL_S + cq * 32, td = lane_addr + COL_DP + cq * 32;
         {
-          uint32_t sv[8], dp[8];
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            __syncwarp();
-            if (keyb + c * 8 < key_lim) {
-              tmem_ld_32x8(ts + c * 8, sv);
-              tmem_ld_32x8(td + c * 8, dp);
-              tmem_ld_wait();
+          // first half (16 keys) in ONE TMEM round trip; its exp math overlaps the previous iteration's
+          // dV / dK / dQ MMAs. Its stores need those MMAs' P / dS operands consumed; they go out before
+          // that iteration's finished accumulators are drained, so the drain's 32 registers never
+          // coexist with pending results.
+          uint32_t sv0[8], dp0[8], sv1[8], dp1[8], pp0[4], dd0[4], pp1[4], dd1[4];
+          __syncwarp();
+          if (keyb < key_lim) {
+            tmem_ld_32x8(ts, sv0);
+            tmem_ld_32x8(td, dp0);
+            if (keyb + 8 < key_lim) {
+              tmem_ld_32x8(ts + 8, sv1);
+              tmem_ld_32x8(td + 8, dp1);
             }
-            sub_chunk(sv, dp, c);
+            tmem_ld_wait();
           }
+          chunk_math(sv0, dp0, 0, pp0, dd0);
+          chunk_math(sv1, dp1, 1, pp1, dd1);
+          if (g > 0) {
+            if (threadIdx.x == 0) TRACE(16 * g + 10);
+            mbar_wait_parked_addr(sbar + 8 * 11, (g - 1) & 1);  // bar_pds_free
+            if (threadIdx.x == 0) TRACE(16 * g + 11);
+            tc_fence_after();
+          }
+          chunk_store(0, pp0, dd0);
+          chunk_store(1, pp1, dd1);
+        }
+        if (g > 0) {
+          if (it == 0) drain(item - static_cast<int>(gridDim.x), nk - 1, true);
+          else if (i == 0) drain(item, j - 1, false);
         }
         {
-          // the last two sub-chunks are fetched together, so S / dP can be handed back to the MMA
-          // warp (next iteration's S / dP) with half of this iteration's exp math still to do
-          uint32_t sv2[8], dp2[8], sv3[8], dp3[8];
+          // the last two sub-chunks are fetched together as well, so S / dP can be handed back to the
+          // MMA warp (next iteration's S / dP) with half of this iteration's exp math still to do
+          uint32_t sv2[8], dp2[8], sv3[8], dp3[8], pp[4], dd[4];
           __syncwarp();
           if (keyb + 16 < key_lim) {
             tmem_ld_32x8(ts + 16, sv2);
@@ -762,8 +771,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_addr(sbar + 8 * 9);  // bar_sdp_read
-          sub_chunk(sv2, dp2, 2);
-          sub_chunk(sv3, dp3, 3);
+          chunk_math(sv2, dp2, 2, pp, dd);
+          chunk_store(2, pp, dd);
+          chunk_math(sv3, dp3, 3, pp, dd);
+          chunk_store(3, pp, dd);
         }
         tc_fence_before();
         fence_proxy_async_smem();
