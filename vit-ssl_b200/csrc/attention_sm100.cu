@@ -21,6 +21,16 @@ namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// per-phase clock64 timelines of CTA 0 (scripts/trace_attn_fwd.py, trace_attn_bwd.py); compiled out by default
+#ifdef VITSSL_ATTN_TRACE
+__device__ long long g_attn_trace[8192];
+#define TRACE(slot) do { if (blockIdx.x == 0 && (slot) < 8192) g_attn_trace[(slot)] = clock64(); } while (0)
+#define FTRACE(slot) do { if (blockIdx.x == 0 && (slot) < 4096) g_attn_trace[4096 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#define FTRACE(slot) do { } while (0)
+#endif
+
 // 16-byte shared-memory store with the state space spelled out
 __device__ __forceinline__ void sts128_(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -148,8 +158,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       int it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         mbar_wait(bar_qk, it & 1);
+        if (lane == 0) FTRACE(16 * it + 0);
         if (it > 0) mbar_wait(bar_oread, (it - 1) & 1);
         tc_fence_after();
+        if (lane == 0) FTRACE(16 * it + 1);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_ss_lo<false>(tmem, q_lo + 2 * k, k_lo + 2 * k, HI, idesc_s, k > 0);
@@ -157,8 +169,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         __syncwarp();
         mbar_wait(bar_p, it & 1);
+        if (lane == 0) FTRACE(16 * it + 2);
         mbar_wait(bar_v, it & 1);
         tc_fence_after();
+        if (lane == 0) FTRACE(16 * it + 3);
         if (elect_one()) {
           for (int ks = 0; ks < ksteps; ++ks)  // P[128, 16 keys] = 8 packed columns per step
             umma_bf16_ts_lo(tmem + FWD_COL_O, tmem + ks * 8, v_lo + ks * 128, HI, idesc_o, ks > 0);
@@ -178,8 +192,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     int it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
+      if (t == 0) FTRACE(16 * it + 7);
       mbar_wait(bar_s, it & 1);
       tc_fence_after();
+      if (t == 0) FTRACE(16 * it + 8);
       // pass 1: row maximum (TMEM loads run one chunk ahead; only the chunk straddling Sk is masked)
       float mx = -INFINITY;
       {
@@ -208,6 +224,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if (c + 1 < nchunks) pass1(rb, ra, c + 1);
         }
       }
+      if (t == 0) FTRACE(16 * it + 9);
       // pass 2: P over S in place (chunk c of 32 fp32 columns -> 16 packed bf16x2 columns at 16c)
       const float mneg = -mx * sl2;
       const f32x2 mnegv = pk2(mneg, mneg);
@@ -243,6 +260,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);  // one arrival per warp
+      if (t == 0) FTRACE(16 * it + 10);
       float sum;
       {
         float s0, s1;
@@ -252,6 +270,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
       mbar_wait(bar_o, it & 1);
       tc_fence_after();
+      if (t == 0) FTRACE(16 * it + 11);
       const int qrow = qt * 128 + t;
       const float inv = 1.0f / sum;
       {
@@ -263,6 +282,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_oread);  // O is in registers: the next item's S MMA may overwrite TMEM
+        if (t == 0) FTRACE(16 * it + 12);
         if constexpr (STAGED) {
           // 32 rows x 64 columns per warp as two 32 x 32 blocks -> swizzled staging -> TMA stores (full
           // 64-byte row segments, clipped at Sq); the rounding residual reuses the blocks afterwards
@@ -270,18 +290,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int row0 = qt * 128 + warp * 32;
           if (lane == 0) tma_store_wait_read<0>();  // the previous item's stores have drained the blocks
           __syncwarp();
+          if (t == 0) FTRACE(16 * it + 4);
           stage_block32<false>(stg, lane, r0, inv);
           stage_block32<false>(stg + 2048, lane, r1, inv);
+          if (t == 0) FTRACE(16 * it + 5);
           fence_proxy_async_smem();
           __syncwarp();
+          if (t == 0) FTRACE(16 * it + 6);
           if (lane == 0) {
             tma_store_3d(&tmap_o, smem + FWD_SMEM_STG + warp * 4096, h * 64, row0, b);
             tma_store_3d(&tmap_o, smem + FWD_SMEM_STG + warp * 4096 + 2048, h * 64 + 32, row0, b);
             tma_store_commit();
           }
+          if (t == 0) FTRACE(16 * it + 14);
           if (p.out_lo) {
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
+            if (t == 0) FTRACE(16 * it + 15);
             stage_block32<true>(stg, lane, r0, inv);
             stage_block32<true>(stg + 2048, lane, r1, inv);
             fence_proxy_async_smem();
@@ -323,6 +348,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qrow] = mx * p.scale + __logf(sum);
         }
       }
+      if (t == 0) FTRACE(16 * it + 13);
     }
   }
   if constexpr (STAGED) {
@@ -349,12 +375,6 @@ struct AttnBwdParams {
   float scale;
 };
 
-#ifdef VITSSL_ATTN_TRACE
-__device__ long long g_attn_trace[8192];
-#define TRACE(slot) do { if (blockIdx.x == 0 && (slot) < 8192) g_attn_trace[(slot)] = clock64(); } while (0)
-#else
-#define TRACE(slot) do { } while (0)
-#endif
 constexpr int BWD_MATH_WARPS = 16;  // 4 per TMEM lane quadrant, 32 of the 128 key columns each
 constexpr int BWD_WARP_MMA = BWD_MATH_WARPS;      // single-thread tcgen05 issuer
 constexpr int BWD_WARP_TMA = BWD_MATH_WARPS + 1;  // single-thread TMA producer
@@ -485,27 +505,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp == BWD_WARP_MMA) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // The whole warp walks the iterations and the barrier waits (uniform control flow) and one elected
+    // lane issues, so every tcgen05.mma is a bare UTCHMMA with uniform-register operands (inside an
+    // `if (lane == 0)` region each one is compiled into its own ELECT / BRA.U.ANY loop). Measured
+    // neutral (159 us either way): the issuing thread is back-pressured by the tensor pipe, which is
+    // itself paced by shared-memory operand reads — S / dP: 8 MMAs x 8 KB of operands = 64 KB, dV / dK /
+    // dQ: 24 x 6 KB = 144 KB per iteration against 128 B/clk, i.e. ~700 + ~1 500 cycles in the trace.
+    {
       constexpr uint32_t idesc_sdp = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_dkv = umma_idesc_bf16(128, 64, true, true);
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, false, true);
       // Descriptor low words (start address >> 4 | leading-byte-offset field) of every operand
       // tile, computed once; advancing inside a tile adds (bytes >> 4). All forms share the high
       // word (SBO = 1024, version 1, 128-byte swizzle).
+      constexpr uint32_t HI = 0x40004040u;
       constexpr uint32_t LBO_K = (16u >> 4) << 16;        // K-major operand
       constexpr uint32_t LBO_MN = (8192u >> 4) << 16;     // MN-major, 64-wide groups 8 KB apart
       constexpr uint32_t LBO_MN2 = (16384u >> 4) << 16;   // MN-major P / dS: key blocks 16 KB apart
       const uint32_t sb = smem_u32(smem) >> 4;
       auto lo = [&](int byte_off, uint32_t lbo) { return (sb + (static_cast<uint32_t>(byte_off) >> 4)) | lbo; };
-      auto mma = [&](uint32_t d_col, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool acc) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-            "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_col),
-            "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(static_cast<uint32_t>(acc)), "r"(0x40004040u)
-            : "memory");
-      };
       // S / dP of iteration `it` of the CTA's n-th item; waits for tiles this iteration uses first
       auto issue_sdp = [&](int n, int it) {
         const int j = it_j(it), i = it_i(it);
@@ -516,11 +534,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_after();
         const uint32_t q_k = lo(BWD_SMEM_Q + slq * BWD_TILE, LBO_K), do_k = lo(BWD_SMEM_DO + slq * BWD_TILE, LBO_K);
         const uint32_t k_k = lo(BWD_SMEM_K + slk * BWD_TILE, LBO_K), v_k = lo(BWD_SMEM_VV + slk * BWD_TILE, LBO_K);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma(COL_S, q_k + 2 * k, k_k + 2 * k, idesc_sdp, k > 0);    // S = Q_i K_j^T
+          for (int k = 0; k < 4; ++k) umma_bf16_ss_lo<false>(COL_S, q_k + 2 * k, k_k + 2 * k, HI, idesc_sdp, k > 0);    // S = Q_i K_j^T
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma(COL_DP, do_k + 2 * k, v_k + 2 * k, idesc_sdp, k > 0);  // dP = dO_i V_j^T
-        umma_commit(bar_sdp_full);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss_lo<false>(COL_DP, do_k + 2 * k, v_k + 2 * k, HI, idesc_sdp, k > 0);  // dP = dO_i V_j^T
+          umma_commit(bar_sdp_full);
+        }
+        __syncwarp();
       };
       // the next item's first S / dP may be issued under the current item's last iteration only
       // if its tiles are released by earlier iterations (true for the 2 x 2 tiling)
@@ -538,32 +559,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const bool early = in_item || early_cross;
           if (have_next && early) {
             mbar_wait(bar_sdp_read, g & 1);
-            TRACE(16 * g + 0);
+            if (lane == 0) TRACE(16 * g + 0);
             tc_fence_after();
             if (in_item) issue_sdp(n, it + 1); else issue_sdp(n + 1, 0);
           }
-          TRACE(16 * g + 1);
+          if (lane == 0) TRACE(16 * g + 1);
           mbar_wait(bar_pds_ready, g & 1);
-          TRACE(16 * g + 2);
+          if (lane == 0) TRACE(16 * g + 2);
           if (i == 0 && kt > 0) mbar_wait(bar_dkv_free, (kt - 1) & 1);  // previous key tile drained
           if (it == 0 && n > 0) mbar_wait(bar_dq_free, (n - 1) & 1);     // previous item's dQ drained
           tc_fence_after();
           const int slq = alt ? (n & 1) : i, slk = alt ? (n & 1) : j;
           const uint32_t q_mn = lo(BWD_SMEM_Q + slq * BWD_TILE, LBO_MN), do_mn = lo(BWD_SMEM_DO + slq * BWD_TILE, LBO_MN);
           const uint32_t k_mn = lo(BWD_SMEM_K + slk * BWD_TILE, LBO_MN);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // dV_j += P^T dO_i   (reduction over the 128 query rows)
-            mma(COL_DV, p_mn + 128 * ks, do_mn + 128 * ks, idesc_dkv, i > 0 || ks > 0);
+            for (int ks = 0; ks < 8; ++ks)  // dV_j += P^T dO_i   (reduction over the 128 query rows)
+              umma_bf16_ss_lo<false>(COL_DV, p_mn + 128 * ks, do_mn + 128 * ks, HI, idesc_dkv, i > 0 || ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // dK_j += dS^T Q_i
-            mma(COL_DK, ds_mn + 128 * ks, q_mn + 128 * ks, idesc_dkv, i > 0 || ks > 0);
+            for (int ks = 0; ks < 8; ++ks)  // dK_j += dS^T Q_i
+              umma_bf16_ss_lo<false>(COL_DK, ds_mn + 128 * ks, q_mn + 128 * ks, HI, idesc_dkv, i > 0 || ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // dQ_i += dS K_j     (reduction over the 128 keys)
-            mma(COL_DQ + i * 64, ds_k + (ks >> 2) * 1024 + (ks & 3) * 2, k_mn + 128 * ks, idesc_dq, j > 0 || ks > 0);
-          umma_commit(bar_pds_free);
-          TRACE(16 * g + 3);
-          if (j == nk - 1) umma_commit(&bar_freeq[slq]);   // last reader of Q_i / dO_i
-          if (i == nq - 1) umma_commit(&bar_freekv[slk]);  // last reader of K_j / V_j
+            for (int ks = 0; ks < 8; ++ks)  // dQ_i += dS K_j     (reduction over the 128 keys)
+              umma_bf16_ss_lo<false>(COL_DQ + i * 64, ds_k + (ks >> 2) * 1024 + (ks & 3) * 2, k_mn + 128 * ks, HI, idesc_dq,
+                                     j > 0 || ks > 0);
+            umma_commit(bar_pds_free);
+            if (j == nk - 1) umma_commit(&bar_freeq[slq]);   // last reader of Q_i / dO_i
+            if (i == nq - 1) umma_commit(&bar_freekv[slk]);  // last reader of K_j / V_j
+          }
+          __syncwarp();
+          if (lane == 0) TRACE(16 * g + 3);
           if (have_next && !early) issue_sdp(n + 1, 0);    // (S / dP were read before P / dS were staged)
           if (i == nq - 1) ++kt;
         }
