@@ -133,3 +133,10 @@ def test_committed_launch_list_reproduces_the_traffic_table(tmp_path):
     for fam in ("gemm_tcgen05_kernel", "ln_kernel", "attn_bwd_kernel", "attn_fwd_kernel"):
         assert got[fam] == want[fam], fam
         assert want[fam]["launches"] > 0 and want[fam]["dram_bytes_per_launch"] > 1e6
+
+
+def test_prefetch_scalar_is_identity_off_gpu():
+    from vit_core._backend.scalar import prefetch_scalar
+    t = torch.ones(())
+    assert prefetch_scalar(t) is t
+    assert prefetch_scalar(3.0) == 3.0

@@ -240,7 +240,9 @@ def test_l1loss_on_model_output_dispatches_to_the_fused_kernel_and_matches_torch
         pred, tg = m(x)
         assert isinstance(pred, MaskedPrediction) and pred.dtype == torch.bfloat16
         loss = torch.nn.L1Loss()(pred, tg)
-    assert "_L1LossFn" in type(loss.grad_fn).__name__ and loss.dtype == torch.float32
+    # (the loss is a PrefetchedScalar: an alias node sits between it and the kernel's autograd node)
+    chain = [type(loss.grad_fn).__name__] + [type(f).__name__ for f, _ in loss.grad_fn.next_functions if f is not None]
+    assert any("_L1LossFn" in n for n in chain) and loss.dtype == torch.float32
     scaler = torch.amp.GradScaler("cuda", init_scale=4096.0)
     scaler.scale(loss).backward()
     g1 = m.simmim_head.weight.grad.clone() / 4096.0
@@ -397,3 +399,48 @@ def test_gpu_knn_matches_sklearn_cosine_knn(Nt, Nv, D, classes):
     assert agree >= 0.995, agree          # identical up to float-rounding of near-tied distances
     res = run_knn_evaluation(xt, yt, xv, yv, classes)
     assert abs(res["accuracy"] - (want == yv).float().mean().item()) <= 0.01 and res["num_neighbors"] == classes
+
+
+@pytest.mark.gpu
+def test_prefetched_loss_scalar_value_autograd_and_ring():
+    """The loss the SimMIM / DINO paths return: `.item()` reads the copy that was enqueued behind the
+    loss kernel (not behind the whole step), with the plain tensor's value, autograd and arithmetic."""
+    from vit_core._backend.scalar import PrefetchedScalar, prefetch_scalar
+    w = torch.randn(64, device="cuda", requires_grad=True)
+    raw = (w * w).sum()
+    loss = prefetch_scalar(raw)
+    assert isinstance(loss, PrefetchedScalar) and loss.data_ptr() == raw.data_ptr()
+    scaled = loss * 3.0
+    assert type(scaled) is torch.Tensor                      # e.g. scaler.scale(loss)
+    scaled.backward()
+    assert torch.allclose(w.grad, 6.0 * w.detach())
+    assert loss.item() == torch.Tensor.item(raw) == float(loss)
+    assert loss.item() == loss.item()                        # second read: remembered float
+    # more outstanding losses than ring slots: the oldest are read before their slot is reused
+    vals = [prefetch_scalar(torch.full((), float(i), device="cuda")) for i in range(80)]
+    assert [v.item() for v in vals] == [float(i) for i in range(80)]
+    # not a scalar / not CUDA: handed back untouched
+    assert type(prefetch_scalar(torch.ones(2, device="cuda"))) is torch.Tensor
+    assert type(prefetch_scalar(torch.ones(()))) is torch.Tensor
+
+
+@pytest.mark.gpu
+def test_simmim_and_dino_losses_are_prefetched():
+    from vit_core._backend.scalar import PrefetchedScalar
+    from vit_core.ssl.dino.loss import DINOLoss
+    from vit_core.ssl.simmim import SimMIMViT
+    torch.manual_seed(0)
+    m = SimMIMViT(num_blocks=1, input_shape=(3, 32, 32), embed_dim=128, patch_size=8, num_heads=2, mlp_dim=256,
+                  dropout=0.0, mask_ratio=0.5).cuda().train()
+    x = torch.rand(4, 3, 32, 32, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred, tgt = m(x)
+        loss = torch.nn.L1Loss()(pred, tgt)
+    assert isinstance(loss, PrefetchedScalar)
+    ref = (pred.detach().float().as_subclass(torch.Tensor) - tgt.float()).abs().mean().item()
+    loss.backward()
+    assert abs(loss.item() - ref) <= 2e-3 * abs(ref)
+    t = torch.randn(2, 4, 512, device="cuda")
+    s = torch.randn(4, 4, 512, device="cuda", requires_grad=True)
+    dl = DINOLoss(0.04, 0.1)(t, s, torch.zeros(512, device="cuda"))
+    assert isinstance(dl, PrefetchedScalar) and dl.item() == torch.Tensor.item(dl)

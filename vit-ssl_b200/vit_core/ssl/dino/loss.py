@@ -9,6 +9,7 @@ from torch import nn
 
 from .._backend_access import Fb
 from ..._backend import eager
+from ..._backend.scalar import prefetch_scalar
 
 
 class DINOLoss(nn.Module):
@@ -38,4 +39,4 @@ class DINOLoss(nn.Module):
         for v0 in range(0, s3.shape[0], 12):
             part = Fb.dino_loss(t3, s3[v0:v0 + 12], center, self.teacher_temp, self.student_temp)
             loss = part if loss is None else loss + part
-        return loss
+        return prefetch_scalar(loss)

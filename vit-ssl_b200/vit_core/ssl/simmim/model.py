@@ -11,6 +11,7 @@ from .._backend_access import Fb, ops
 from ...encoder_block import EncoderBlock
 from .masking import draw_mask
 from ..._backend import dp, eager
+from ..._backend.scalar import prefetch_scalar
 
 
 class MaskedPrediction(torch.Tensor):
@@ -41,7 +42,7 @@ def _fused_l1(input, target, size_average=None, reduce=None, reduction="mean", w
     with torch._C.DisableTorchFunctionSubclass():
         pred = input.as_subclass(torch.Tensor)
         tgt = target.as_subclass(torch.Tensor)
-        return Fb.l1_loss(pred, tgt)
+        return prefetch_scalar(Fb.l1_loss(pred, tgt))
 
 
 class SimMIMViT(nn.Module):
@@ -91,7 +92,7 @@ class SimMIMViT(nn.Module):
         dp.maybe_attach(self)  # data parallel under torchrun without touching the trainer
         masked, targets, _ = self._encode_masked(x)
         pred = Fb.mlp(masked, [self.simmim_head], [False])
-        return Fb.l1_loss(pred, targets)
+        return prefetch_scalar(Fb.l1_loss(pred, targets))
 
     @torch.no_grad()
     @eager
