@@ -287,6 +287,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
+    def wait_ready(self, timeout):
+        t_end = time.time() + timeout
+        while self.proc is not None and len(self.rows) < 2 and time.time() < t_end and self.proc.poll() is None:
+            time.sleep(0.05)
+
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
@@ -414,6 +419,11 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        # nvidia-smi attaches to the driver for ~0.5 s (seconds in the first process on a fresh box) and
+        # kernel launches crawl meanwhile: a timed region that overlaps it measured 16.8 instead of 14.8
+        # ms/step. Wait for its first rows before anything is timed.
+        sampler.wait_ready(20.0)
+    barrier()
     for i in range(args.warmup):
         step(dev_in[i % n_host])
     barrier()
@@ -441,6 +451,7 @@ def run_gpu_arm(args):
 
     # ---- timed region 2: end to end (pinned host -> device each step, loss read back each step) ----
     copy_stream = torch.cuda.Stream()
+    h2d_gbps = []
 
     def e2e_run(host_sets):
         bufs = [[torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host_sets[0]] for _ in range(2)]
@@ -454,9 +465,24 @@ def run_gpu_arm(args):
                     b_.copy_(h, non_blocking=True)
                 ready[i % 2].record(copy_stream)
 
+        # pinned host -> device bandwidth of this box (reported next to e2e: a slow link shows here first)
+        with torch.cuda.stream(copy_stream):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 0.0
+            for _ in range(3):
+                c0.record(copy_stream)
+                for b_, h in zip(bufs[0], host_sets[0]):
+                    b_.copy_(h, non_blocking=True)
+                c1.record(copy_stream)
+                c1.synchronize()
+                nbytes = sum(h.numel() * h.element_size() for h in host_sets[0])
+                best = max(best, nbytes / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+        h2d_gbps.append(round(best, 1))
         for ev in free:
             ev.record()
-        for i in range(2):  # warm the path (first u8 step builds nothing new, but keep regions alike)
+        # W warm-up steps of the SAME loop (copies included): on a fresh box the first process measured
+        # 1.3-1.9 ms/step more in this region than later ones with only two (host pages / PCIe link warm-up)
+        for i in range(max(2, args.warmup)):
             prefetch(i)
             torch.cuda.current_stream().wait_event(ready[i % 2])
             step(bufs[i % 2]).item()
@@ -595,9 +621,9 @@ def run_gpu_arm(args):
             "model_tflops": round(value * fl["step"] / 1e12, 1),
             "mfu_vs_sustained_bf16": round(value / world * fl["step"] / 1e12 / peaks()["tf_sustained"], 4),
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": round(e2e_ms, 3), "input": "fp32 images from pinned host memory (ToTensor output, what the reference's loaders yield)"},
+                    "ms_per_step": round(e2e_ms, 3), "h2d_gbps": h2d_gbps[0], "input": "fp32 images from pinned host memory (ToTensor output, what the reference's loaders yield)"},
             "e2e_u8": {"value": round(e2e8_value, 1), "unit": "images/s", "h2d_bytes_per_step": in_bytes // 4, "d2h_bytes_per_step": 4,
-                       "ms_per_step": round(e2e8_ms, 3), "input": "raw uint8 images from pinned host memory, /255 inside the patch kernels (SURVEY 8(f)3)"},
+                       "ms_per_step": round(e2e8_ms, 3), "h2d_gbps": h2d_gbps[1], "input": "raw uint8 images from pinned host memory, /255 inside the patch kernels (SURVEY 8(f)3)"},
             "gpu_launches": int(launches), "host_issue_ms_per_step": round(host_issue_ms, 3),
             "loss": round(final_loss, 5), "clocks": clocks,
         }
