@@ -374,7 +374,10 @@ def run_gpu_arm(args):
     dev_in = [[h.to(dev) for h in hs] for hs in host]
     in_bytes = sum(h.numel() * 4 for h in host[0])
 
+    phases = []  # host seconds per phase of every step (diagnostic)
+
     def step(batch, objective="dropin"):
+        t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             if wl == "simmim":
@@ -386,11 +389,16 @@ def run_gpu_arm(args):
             else:
                 t, s = model(batch, 2)
                 loss = crit(t.view(2, B, -1), s.view(8, B, -1), model.center)
+        t1 = time.perf_counter()
         scaler.scale(loss).backward()
+        t2 = time.perf_counter()
         scaler.step(opt)
+        t3 = time.perf_counter()
         scaler.update()
         if wl == "dino":
             model.momentum_update_teacher(0.996)
+        t4 = time.perf_counter()
+        phases.append((round((t1 - t0) * 1e3, 2), round((t2 - t1) * 1e3, 2), round((t3 - t2) * 1e3, 2), round((t4 - t3) * 1e3, 2)))
         return loss
 
     def barrier():
@@ -405,15 +413,37 @@ def run_gpu_arm(args):
             return float(t.item())
         return ms
 
+    import gc
+    gc_log = []       # (generation, ms) of every collector run inside a timed() call
+
+    def _gc_cb(phase, info, _t=[0.0]):
+        if phase == "start":
+            _t[0] = time.perf_counter()
+        else:
+            gc_log.append((info.get("generation"), round((time.perf_counter() - _t[0]) * 1e3, 2)))
+    gc.callbacks.append(_gc_cb)
+    step_events = []  # per-step device times of the last timed() call (diagnostic: are slow regions a few stalls?)
+    host_steps = []   # per-step host issue times of the same call
+
     def timed(n, fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        del host_steps[:]
+        del gc_log[:]
+        del phases[:]
+        ops.HOST_TRACE = []
         barrier()
         e0.record()
+        marks[0].record()
         out = None
         for i in range(n):
+            th = time.perf_counter()
             out = fn(i)
+            marks[i + 1].record()
+            host_steps.append((time.perf_counter() - th) * 1e3)
         e1.record()
         barrier()
+        step_events[:] = [marks[i].elapsed_time(marks[i + 1]) for i in range(n)]
         return max_over_ranks(e0.elapsed_time(e1)), out
 
     sampler = ClockSampler(local)
@@ -424,16 +454,24 @@ def run_gpu_arm(args):
         # ms/step. Wait for its first rows before anything is timed.
         sampler.wait_ready(20.0)
     barrier()
-    for i in range(args.warmup):
-        step(dev_in[i % n_host])
-    barrier()
+    # warm-up = a rehearsal of the timed loop itself (same retention of the previous step's loss object,
+    # same run-ahead of the host): the caching allocator must reach its steady state here. With a bare
+    # `step()` loop it still grew by three cudaMalloc calls in the second timed step (1-340 ms each)
+    timed(args.warmup, lambda i: step(dev_in[i % n_host]))
 
     # ---- timed region 1: device-resident inputs (3 rotating batches + GBs of activations >> L2) ----
     lib.launch_count(reset=True)
+    ms0 = torch.cuda.memory_stats()
     t_host0 = time.time()
     ms_total, loss = timed(args.steps, lambda i: step(dev_in[i % n_host]))
     launches = lib.launch_count()
     t_host1 = time.time()
+    per_step = {"device_ms": [round(v, 2) for v in step_events], "host_issue_ms": [round(v, 2) for v in host_steps],
+                "loadavg_1min": round(os.getloadavg()[0], 2), "gc_runs": [g for g in gc_log if g[1] >= 1.0], "phases_fwd_bwd_opt_upd_ms": phases[:4], "stack_bwd_c_ms": [v for _, v in (ops.HOST_TRACE or [])[:4]],
+                "cuda_malloc_calls": torch.cuda.memory_stats().get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0),
+                "cuda_free_calls": torch.cuda.memory_stats().get("num_device_free", 0) - ms0.get("num_device_free", 0),
+                "reserved_gb": round(torch.cuda.memory_reserved() / 2**30, 2)}
+    ops.HOST_TRACE = None
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
     final_loss = float(loss.detach())
@@ -452,6 +490,7 @@ def run_gpu_arm(args):
     # ---- timed region 2: end to end (pinned host -> device each step, loss read back each step) ----
     copy_stream = torch.cuda.Stream()
     h2d_gbps = []
+    e2e_diag = []
 
     def e2e_run(host_sets):
         bufs = [[torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host_sets[0]] for _ in range(2)]
@@ -480,27 +519,36 @@ def run_gpu_arm(args):
         h2d_gbps.append(round(best, 1))
         for ev in free:
             ev.record()
-        # W warm-up steps of the SAME loop (copies included): on a fresh box the first process measured
-        # 1.3-1.9 ms/step more in this region than later ones with only two (host pages / PCIe link warm-up)
-        for i in range(max(2, args.warmup)):
-            prefetch(i)
-            torch.cuda.current_stream().wait_event(ready[i % 2])
-            step(bufs[i % 2]).item()
-            free[i % 2].record()
+        walls = []
+
+        def loop(nsteps):
+            # the trainers' loop: next batch's copy in flight on the copy stream, step, loss read back
+            prefetch(0)
+            for i in range(nsteps):
+                tw = time.perf_counter()
+                if i + 1 < nsteps:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[i % 2])
+                l = step(bufs[i % 2])
+                free[i % 2].record()
+                _ = l.item()  # device -> host read of the step's loss, as the trainer does every step
+                walls.append(round((time.perf_counter() - tw) * 1e3, 2))
+
+        # W warm-up steps of the SAME loop (copies, look-ahead and loss retention included): on a fresh box
+        # the first process measured 1.3-1.9 ms/step more in this region with a simpler warm-up
+        loop(max(2, args.warmup))
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
+        del gc_log[:]
+        del walls[:]
         t0.record()
-        prefetch(0)
-        for i in range(args.steps):
-            if i + 1 < args.steps:
-                prefetch(i + 1)
-            torch.cuda.current_stream().wait_event(ready[i % 2])
-            l = step(bufs[i % 2])
-            free[i % 2].record()
-            _ = l.item()  # device -> host read of the step's loss, as the trainer does every step
+        loop(args.steps)
         t1.record()
         barrier()
         ms = max_over_ranks(t0.elapsed_time(t1))
+        e2e_diag.append({"wall_ms": walls, "cuda_malloc_calls": torch.cuda.memory_stats().get("num_device_alloc", 0) - m0,
+                         "gc_runs": [g for g in gc_log if g[1] >= 1.0]})
         return world * B * args.steps / (ms / 1e3), ms / args.steps
 
     e2e_value, e2e_ms = e2e_run(host)
@@ -509,8 +557,7 @@ def run_gpu_arm(args):
     # ---- the fused-objective entry (non-reference API), device-resident, for comparison ----
     fused = None
     if wl == "simmim":
-        for i in range(2):
-            step(dev_in[i % n_host], "fused")
+        timed(max(2, args.warmup), lambda i: step(dev_in[i % n_host], "fused"))
         ms_f, _ = timed(args.steps, lambda i: step(dev_in[i % n_host], "fused"))
         fused = {"value": round(world * B * args.steps / (ms_f / 1e3), 1), "unit": "images/s",
                  "ms_per_step": round(ms_f / args.steps, 3), "api": "SimMIMViT.reconstruction_loss(x) (targets never materialised for the caller)"}
@@ -621,10 +668,10 @@ def run_gpu_arm(args):
             "model_tflops": round(value * fl["step"] / 1e12, 1),
             "mfu_vs_sustained_bf16": round(value / world * fl["step"] / 1e12 / peaks()["tf_sustained"], 4),
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": round(e2e_ms, 3), "h2d_gbps": h2d_gbps[0], "input": "fp32 images from pinned host memory (ToTensor output, what the reference's loaders yield)"},
+                    "ms_per_step": round(e2e_ms, 3), "h2d_gbps": h2d_gbps[0], "per_step": e2e_diag[0], "input": "fp32 images from pinned host memory (ToTensor output, what the reference's loaders yield)"},
             "e2e_u8": {"value": round(e2e8_value, 1), "unit": "images/s", "h2d_bytes_per_step": in_bytes // 4, "d2h_bytes_per_step": 4,
                        "ms_per_step": round(e2e8_ms, 3), "h2d_gbps": h2d_gbps[1], "input": "raw uint8 images from pinned host memory, /255 inside the patch kernels (SURVEY 8(f)3)"},
-            "gpu_launches": int(launches), "host_issue_ms_per_step": round(host_issue_ms, 3),
+            "gpu_launches": int(launches), "host_issue_ms_per_step": round(host_issue_ms, 3), "per_step": per_step,
             "loss": round(final_loss, 5), "clocks": clocks,
         }
         for k, v in (("fused_objective", fused), ("roofline", roof), ("roofline_attn", roof_attn), ("roofline_hbm", roof_hbm),

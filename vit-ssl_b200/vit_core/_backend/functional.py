@@ -185,6 +185,17 @@ import os as _os
 DP_STACK_CHUNKS = int(_os.environ.get("VITSSL_DP_CHUNKS", "4"))
 
 
+def _take_saved(ctx):
+    """The tensors a node stored as `ctx.saved`, released from the node: like autograd's own saved tensors
+    they are gone after the first backward, so a loss object that outlives its step (the trainers keep
+    `loss` until the next iteration assigns it) does not pin this step's buffers during the next forward."""
+    saved, ctx.saved = ctx.saved, None
+    if saved is None:
+        raise RuntimeError("vit_core: trying to backward through the graph a second time (the node's saved "
+                           "buffers were released by the first backward; retain_graph is not supported by the fused nodes)")
+    return saved
+
+
 class _EncoderStackFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, meta, *params):
@@ -277,7 +288,7 @@ class _EncoderStackFn(torch.autograd.Function):
                 if not need:
                     grads[i] = None
             return (dx if ctx.needs_input_grad[0] else None, None, *grads)
-        meta, params, saved = ctx.meta, ctx.params, ctx.saved
+        meta, params, saved = ctx.meta, ctx.params, _take_saved(ctx)
         L, H = meta.L, meta.H
         B, S, D = ctx.shape
         M = B * S
@@ -569,7 +580,7 @@ class _MHAFn(torch.autograd.Function):
     def backward(ctx, gout, *_):
         meta = ctx.meta
         H = meta.H
-        qb, kb, vb, q, k, v, ctx_, lse, ctx_lo = ctx.saved
+        qb, kb, vb, q, k, v, ctx_, lse, ctx_lo = _take_saved(ctx)
         wqkv, wob = meta.weights
         B, Sq, D = q.shape
         Sk = k.shape[1]
@@ -634,7 +645,7 @@ class _SDPAFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout, *_):
-        qb, kb, vb, out, lse = ctx.saved
+        qb, kb, vb, out, lse = _take_saved(ctx)
         go = _as_bf16(gout.reshape(out.shape))
         dq, dk, dv = ops.attention_generic_bwd(qb, kb, vb, out, go, lse, ctx.scale)
         qs, ks, vs = ctx.shapes
@@ -664,7 +675,7 @@ class _LayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        x2, mean, rstd, gamma = ctx.saved
+        x2, mean, rstd, gamma = _take_saved(ctx)
         dy = _as_bf16(gout.reshape(-1, gout.shape[-1]))
         dx, _, dg, db = ops.add_layernorm_bwd(dy, x2, mean, rstd, gamma, None)
         return dx.view(ctx.in_shape).to(ctx.in_dtype), dg, db, None
@@ -719,7 +730,7 @@ class _EmbedFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gx):
-        (patches,) = ctx.saved
+        (patches,) = _take_saved(ctx)
         meta = ctx.meta
         B, N, D = ctx.dims
         wshape, cshape, pshape, mshape = ctx.shapes
@@ -851,7 +862,7 @@ class _GatherRowsFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        (inv_idx,) = ctx.saved
+        (inv_idx,) = _take_saved(ctx)
         B, S, D = ctx.shape
         return ops.scatter_rows_f32(_as_bf16(gy), inv_idx, B * S).view(B, S, D), None, None
 
@@ -872,7 +883,7 @@ class _L1LossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, go):
-        (sign,) = ctx.saved
+        (sign,) = _take_saved(ctx)
         d = ops.l1_loss_bwd(sign, go)  # one pass: sign * (go / n), go read on the device
         return (d if ctx.dt == torch.bfloat16 else d.to(ctx.dt)), None
 
@@ -900,7 +911,7 @@ class _NormLinearWNFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gl):
-        zb, zn, inv_z, w, inv_v, g, v = ctx.saved
+        zb, zn, inv_z, w, inv_v, g, v = _take_saved(ctx)
         dl = _as_bf16(gl)
         dzn = ops.gemm(dl, w, b_mn=True)
         dz = ops.l2norm_bwd(zb, inv_z, dzn)
@@ -929,7 +940,7 @@ class _DinoLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, go):
-        tb, sb, c, t_stats, s_lse = ctx.saved
+        tb, sb, c, t_stats, s_lse = _take_saved(ctx)
         tt, ts = ctx.temps
         ds = ops.dino_loss_bwd(tb, sb, c, t_stats, s_lse, go, tt, ts)
         return None, ds.to(ctx.dt), None, None, None

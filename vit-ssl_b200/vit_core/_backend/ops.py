@@ -692,6 +692,9 @@ _STACK_GRAD_SHAPES = lambda D, F_: (("dwqkv", (3 * D, D)), ("dwo", (D, D)), ("dw
                                     ("dbe2", (D,)))
 
 
+HOST_TRACE = None  # developer diagnostic: set to a list to collect host times of the stack's C calls
+
+
 class EncoderStackBackward:
     """Backward of one `encoder_stack_fwd` call, runnable as descending layer ranges.
 
@@ -741,6 +744,12 @@ class EncoderStackBackward:
 
     def run(self, l_begin, l_end):
         self.args.l_begin, self.args.l_end = int(l_begin), int(l_end)
+        if HOST_TRACE is not None:
+            import time as _t
+            t0 = _t.perf_counter()
+            _l.call("vitssl_encoder_stack_bwd", _ct.addressof(self.args), _l.stream_ptr())
+            HOST_TRACE.append(("stack_bwd_c_call_ms", round((_t.perf_counter() - t0) * 1e3, 2)))
+            return
         _l.call("vitssl_encoder_stack_bwd", _ct.addressof(self.args), _l.stream_ptr())
 
     def flat_slice(self, l_begin, l_end):
