@@ -918,8 +918,12 @@ static int gemm_impl(const void* A, const void* B, void* C, int64_t M, int64_t N
   // bound by HBM and the epilogue, so those stay single-CTA. VITSSL_GEMM_PAIR=0/1/2 = off/auto/force.
   // An MN-major B operand is staged in 64-column boxes, so its per-CTA half must be a multiple of 64.
   static const int pair_env = getenv("VITSSL_GEMM_PAIR") ? atoi(getenv("VITSSL_GEMM_PAIR")) : 1;
+  // Round 2, re-measured at the ViT-S shapes with pairs forced: the long-K plain / bias GEMMs gain
+  // (FFN2 forward 50176x384x1536: 66.1 -> 59.8 us, FFN1 dgrad 64.5 -> 61.5, QKV dgrad 51.4 -> 49.0),
+  // the arithmetic-heavy epilogues (GELU forms, MUL), K = 384 and the weight gradients do not.
+  const bool long_k_plain = K >= 1024 && N >= 256 && !a_mn && (epilogue == VITSSL_EPI_NONE || epilogue == VITSSL_EPI_BIAS);
   bool pair = pair_env != 0 && M >= 1024 && (M % 256 == 0 || M >= 4096) && N >= 128 &&
-              (pair_env == 2 || (N >= 512 && K >= 512));
+              (pair_env == 2 || (N >= 512 && K >= 512) || long_k_plain);
   if (pair) {
     if (bn == 64) pair = false;
     if (b_mn && bn == 192) bn = 128;
