@@ -23,7 +23,10 @@ def _ref(qkv, B, S, H):
     return q, k, v, ctx, probs
 
 
-@pytest.mark.parametrize("B,S,H", [(2, 196, 6), (3, 197, 6), (2, 37, 3), (1, 256, 2), (2, 128, 1), (5, 16, 4), (2, 144, 6), (1, 1, 1), (2, 129, 2)])
+# short sequences are packed several images per 128-row tile (block-diagonal attention): B = 7, S = 37 -> groups of
+# 3 with a remainder of 1; B = 5, S = 50 -> pairs; B = 9, S = 17 -> groups of 7; B = 4, S = 64 -> exactly two per tile
+@pytest.mark.parametrize("B,S,H", [(2, 196, 6), (3, 197, 6), (2, 37, 3), (1, 256, 2), (2, 128, 1), (5, 16, 4), (2, 144, 6), (1, 1, 1), (2, 129, 2),
+                                   (7, 37, 2), (5, 50, 1), (9, 17, 2), (4, 64, 1), (3, 65, 1)])
 def test_attention_tcgen05_fwd_bwd(B, S, H):
     ops = _ops()
     D = H * 64

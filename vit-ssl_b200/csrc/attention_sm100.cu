@@ -68,6 +68,11 @@ struct AttnFwdParams {
   int B, H, Sq, Sk, kv_rows;          // kv_rows = round_up(Sk, 16) <= 256
   float scale;
   int staged;                         // 1: context leaves through shared-memory staging + TMA stores
+  // Packed short sequences (self-attention, S <= 64: DINO local crops, cfg 1): G = 128 / S images share
+  // one 128-row tile. The token rows of consecutive images are contiguous ([B*S] rows), so the tile is
+  // simply rows [g*G*S, g*G*S + 128) of that matrix and the attention becomes block-diagonal with
+  // block size S; rows past G*S belong to the next group and are masked / never stored.
+  int G, GS;                          // images per tile (1 = one image per tile), G * S
 };
 
 constexpr int FWD_THREADS = 192;  // warps 0-3 softmax (TMEM lane quadrant = warp), 4 = TMA, 5 = MMA
@@ -86,7 +91,9 @@ constexpr uint32_t FWD_COL_O = 128;  // O accumulator columns [128,192): inside 
 //              back over S in TMEM as packed bf16 (tcgen05.st), then O / rowsum -> global.
 // Nothing of the S x S probability matrix ever reaches shared or global memory
 // (attention.py:20-23 materialises it three times).
-template <bool STAGED>  // context leaves through staging + TMA stores (S > 64) or per-thread stores
+// STAGED: context leaves through staging + TMA stores (S > 64) or per-thread stores.
+// PACKED: several short sequences per tile (see AttnFwdParams::G), always with per-thread stores.
+template <bool STAGED, bool PACKED>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
@@ -108,8 +115,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nq = (p.Sq + 127) / 128;
-  const int items = p.B * p.H * nq;
+  constexpr bool packed = PACKED;
+  const int nq = (p.Sq + 127) / 128;                                        // 1 when packed
+  const int items = (packed ? (p.B + p.G - 1) / p.G : p.B) * p.H * nq;      // packed: (group, head)
 
   if (warp == 4) {
     if (lane == 0) {
@@ -135,13 +143,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       int it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
+        // packed: b is the group index, the maps are [B*S] rows x 1 batch
+        const int qrow0 = packed ? b * p.GS : qt * 128, krow0 = packed ? b * p.GS : 0, bc = packed ? 0 : b;
         if (it > 0) mbar_wait(bar_s, (it - 1) & 1);
         mbar_expect_tx(bar_qk, 16384u + kv_bytes);
-        tma_load_3d(sQ, &tmap_q, bar_qk, h * 64, qt * 128, b);
-        tma_load_3d(sK, &tmap_k, bar_qk, h * 64, 0, b);
+        tma_load_3d(sQ, &tmap_q, bar_qk, h * 64, qrow0, bc);
+        tma_load_3d(sK, &tmap_k, bar_qk, h * 64, krow0, bc);
         if (it > 0) mbar_wait(bar_o, (it - 1) & 1);
         mbar_expect_tx(bar_v, kv_bytes);
-        tma_load_3d(sV, &tmap_v, bar_v, h * 64, 0, b);
+        tma_load_3d(sV, &tmap_v, bar_v, h * 64, krow0, bc);
       }
     }
   } else if (warp == 5) {
@@ -189,6 +199,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const float sl2 = p.scale * kLog2e;
     const f32x2 sl2v = pk2(sl2, sl2);
     const int nchunks = (p.kv_rows + 31) / 32;
+    // this thread's valid key columns [clo, chi): all Sk keys, or (packed) the S keys of its own image
+    int clo = 0, chi = p.Sk;
+    if (packed) {
+      const int gi = t / p.Sq;
+      clo = t < p.GS ? gi * p.Sq : 0;
+      chi = t < p.GS ? clo + p.Sq : 0;
+    }
+    const unsigned clen = static_cast<unsigned>(chi - clo);
+    auto col_ok = [&](int col) { return packed ? static_cast<unsigned>(col - clo) < clen : col < chi; };
+    auto chunk_full = [&](int c) { return packed ? (c * 32 >= clo && c * 32 + 32 <= chi) : c * 32 + 32 <= chi; };
+    auto chunk_none = [&](int c) { return packed && (c * 32 + 32 <= clo || c * 32 >= chi); };
     int it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
@@ -205,7 +226,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         auto pass1 = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
           tmem_ld_wait();
           if (c + 1 < nchunks) tmem_ld_32x32(lane_addr + (c + 1) * 32, nxt);
-          if (c * 32 + 32 <= p.Sk) {
+          if (chunk_none(c)) {
+            // (packed) none of this chunk's keys belong to this row's image
+          } else if (chunk_full(c)) {
             float m0 = __uint_as_float(cur[0]), m1 = __uint_as_float(cur[1]);
 #pragma unroll
             for (int i = 2; i < 32; i += 2) {
@@ -216,7 +239,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < p.Sk) mx = fmaxf(mx, __uint_as_float(cur[i]));
+              if (col_ok(c * 32 + i)) mx = fmaxf(mx, __uint_as_float(cur[i]));
           }
         };
         for (int c = 0; c < nchunks; c += 2) {
@@ -236,18 +259,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tmem_ld_wait();
           if (c + 1 < nchunks) tmem_ld_32x32(lane_addr + (c + 1) * 32, nxt);
           uint32_t pk[16];
-          const bool full = c * 32 + 32 <= p.Sk;
+          const bool full = chunk_full(c);
+          if (chunk_none(c)) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float a0, a1;
-            upk2(ffma2(pk2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2v, mnegv), a0, a1);
-            float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
-            if (!full) {
-              e0 = (c * 32 + i < p.Sk) ? e0 : 0.f;
-              e1 = (c * 32 + i + 1 < p.Sk) ? e1 : 0.f;
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float a0, a1;
+              upk2(ffma2(pk2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2v, mnegv), a0, a1);
+              float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+              if (!full) {
+                e0 = col_ok(c * 32 + i) ? e0 : 0.f;
+                e1 = col_ok(c * 32 + i + 1) ? e1 : 0.f;
+              }
+              sum2 = fadd2(sum2, pk2(e0, e1));  // fp32 row sum: exact LSE for the backward recomputation
+              pk[i >> 1] = pack_bf16(e0, e1);
             }
-            sum2 = fadd2(sum2, pk2(e0, e1));  // fp32 row sum: exact LSE for the backward recomputation
-            pk[i >> 1] = pack_bf16(e0, e1);
           }
           tmem_st_32x16(lane_addr + c * 16, pk);
         };
@@ -271,7 +299,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(bar_o, it & 1);
       tc_fence_after();
       if (t == 0) FTRACE(16 * it + 11);
-      const int qrow = qt * 128 + t;
+      // packed: row t of the tile is global token row b * GS + t (b = group index)
+      const int qrow = packed ? t : qt * 128 + t;
+      const long long grow = packed ? static_cast<long long>(b) * p.GS + t : 0;
+      const bool row_ok = packed ? (t < p.GS && grow < static_cast<long long>(p.B) * p.Sq) : qrow < p.Sq;
       const float inv = 1.0f / sum;
       {
         uint32_t r0[32], r1[32];
@@ -319,8 +350,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
           if (qrow < p.Sq && p.lse)
             p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qrow] = mx * p.scale + __logf(sum);
-        } else if (qrow < p.Sq) {
-          const long long ooff = (static_cast<long long>(b) * p.Sq + qrow) * p.ldo + h * 64;
+        } else if (row_ok) {
+          const long long ooff = (packed ? grow : static_cast<long long>(b) * p.Sq + qrow) * p.ldo + h * 64;
           __nv_bfloat16* op = p.out + ooff;
           // 8 context values -> 16 bytes of bf16, and (training) 16 bytes of their bf16 rounding
           // residuals: hi + lo carries 16 significant bits of O, which the backward's
@@ -344,8 +375,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           for (int i = 0; i < 32; i += 8) emit8(r0, i, i);
 #pragma unroll
           for (int i = 0; i < 32; i += 8) emit8(r1, i, 32 + i);
-          if (p.lse)
-            p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qrow] = mx * p.scale + __logf(sum);
+          if (p.lse) {
+            const long long bi = packed ? grow / p.Sq : b;                 // image, token inside it
+            const long long ti = packed ? grow - bi * p.Sq : qrow;
+            p.lse[(bi * p.H + h) * p.Sq + ti] = mx * p.scale + __logf(sum);
+          }
         }
       }
       if (t == 0) FTRACE(16 * it + 13);
@@ -373,6 +407,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dv; long long lddv;
   int B, H, Sq, Sk;
   float scale;
+  int G, GS;  // packed short sequences: images per 128-row tile and G * S (see AttnFwdParams::G)
 };
 
 constexpr int BWD_MATH_WARPS = 16;  // 4 per TMEM lane quadrant, 32 of the 128 key columns each
@@ -414,12 +449,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 //               operands, and drain dV/dK (per key tile) and dQ (per item) from TMEM.
 // With a single 128x128 tile per item (S <= 128, the DINO local crops) the items alternate
 // between the two tile slots, so loads are double-buffered there too.
+// PACKED (S <= 64 self-attention): G images per tile. Their token rows are contiguous, so the tile of
+// group g is rows [g*G*S, +128) of the [B*S] row matrix, one iteration per item, and P / dS are
+// block-diagonal with block size S; rows and keys past G*S belong to the next group: masked, and
+// never stored (the last partly valid 32-row block of an accumulator leaves through the *_t maps,
+// whose box has G*S % 32 rows).
+template <bool PACKED>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_dq,
                 const __grid_constant__ CUtensorMap tmap_dk, const __grid_constant__ CUtensorMap tmap_dv,
+                const __grid_constant__ CUtensorMap tmap_dq_t,
+                const __grid_constant__ CUtensorMap tmap_dk_t, const __grid_constant__ CUtensorMap tmap_dv_t,
                 const AttnBwdParams p) {
+  constexpr bool packed = PACKED;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -441,7 +485,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int nq = (p.Sq + 127) >> 7, nk = (p.Sk + 127) >> 7;  // each 1 or 2
   const int nit = nq * nk;
   const bool alt = nit == 1;  // single-tile items alternate between the two slots
-  const int items = p.B * p.H;
+  const int items = (packed ? (p.B + p.G - 1) / p.G : p.B) * p.H;  // packed: (group, head)
   // iteration it -> (key tile j, query tile i), j outer
   auto it_j = [&](int it) { return nq == 2 ? it >> 1 : it; };
   auto it_i = [&](int it) { return nq == 2 ? it & 1 : 0; };
@@ -451,6 +495,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k);
       tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
       tma_prefetch_desc(&tmap_dq); tma_prefetch_desc(&tmap_dk); tma_prefetch_desc(&tmap_dv);
+      if (packed) { tma_prefetch_desc(&tmap_dq_t); tma_prefetch_desc(&tmap_dk_t); tma_prefetch_desc(&tmap_dv_t); }
       for (int i = 0; i < 8; ++i) mbar_init(bar + i, 1);
       mbar_init(bar_sdp_full, 1); mbar_init(bar_sdp_read, BWD_MATH_WARPS);
       mbar_init(bar_pds_ready, BWD_MATH_WARPS); mbar_init(bar_pds_free, 1);
@@ -486,15 +531,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int sl = alt ? (n & 1) : j;
           if (u > 0) mbar_wait_parked(&bar_freekv[sl], (u - 1) & 1);
           mbar_expect_tx(&bar_ldkv[sl], 2 * BWD_TILE);
-          tma_load_3d(smem + BWD_SMEM_K + sl * BWD_TILE, &tmap_k, &bar_ldkv[sl], h * 64, j * 128, b);
-          tma_load_3d(smem + BWD_SMEM_VV + sl * BWD_TILE, &tmap_v, &bar_ldkv[sl], h * 64, j * 128, b);
+          tma_load_3d(smem + BWD_SMEM_K + sl * BWD_TILE, &tmap_k, &bar_ldkv[sl], h * 64, packed ? b * p.GS : j * 128, packed ? 0 : b);
+          tma_load_3d(smem + BWD_SMEM_VV + sl * BWD_TILE, &tmap_v, &bar_ldkv[sl], h * 64, packed ? b * p.GS : j * 128, packed ? 0 : b);
         };
         auto load_q = [&](int i) {
           const int sl = alt ? (n & 1) : i;
           if (u > 0) mbar_wait_parked(&bar_freeq[sl], (u - 1) & 1);
           mbar_expect_tx(&bar_ldq[sl], 2 * BWD_TILE);
-          tma_load_3d(smem + BWD_SMEM_Q + sl * BWD_TILE, &tmap_q, &bar_ldq[sl], h * 64, i * 128, b);
-          tma_load_3d(smem + BWD_SMEM_DO + sl * BWD_TILE, &tmap_do, &bar_ldq[sl], h * 64, i * 128, b);
+          tma_load_3d(smem + BWD_SMEM_Q + sl * BWD_TILE, &tmap_q, &bar_ldq[sl], h * 64, packed ? b * p.GS : i * 128, packed ? 0 : b);
+          tma_load_3d(smem + BWD_SMEM_DO + sl * BWD_TILE, &tmap_do, &bar_ldq[sl], h * 64, packed ? b * p.GS : i * 128, packed ? 0 : b);
         };
         // in the order the slots are released by the previous item and first needed by this one
         load_kv(0);
@@ -650,8 +695,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       stage32(smem_u32(stg), v, sel == 0 ? 1.0f : p.scale);
       fence_proxy_async_smem();
       __syncwarp();
+      // packed: only the G*S rows of this group may be written (the tile's remaining rows are the next
+      // group's): whole 32-row blocks through the 32-row maps, the partly valid one through the tail maps
+      const int prow = b * p.GS + row0, pvalid = p.GS - row0;
       if (lane == 0) {
-        tma_store_3d(sel == 0 ? &tmap_dv : &tmap_dk, stg, col0, j * 128 + row0, b);
+        if (!packed) tma_store_3d(sel == 0 ? &tmap_dv : &tmap_dk, stg, col0, j * 128 + row0, b);
+        else if (pvalid >= 32) tma_store_3d(sel == 0 ? &tmap_dv : &tmap_dk, stg, col0, prow, 0);
+        else if (pvalid > 0) tma_store_3d(sel == 0 ? &tmap_dv_t : &tmap_dk_t, stg, col0, prow, 0);
         tma_store_commit();
       }
       if (item_done) {
@@ -670,7 +720,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmap_dq, stg, col0, sel * 128 + row0, b);
+            if (!packed) tma_store_3d(&tmap_dq, stg, col0, sel * 128 + row0, b);
+            else if (pvalid >= 32) tma_store_3d(&tmap_dq, stg, col0, prow, 0);
+            else if (pvalid > 0) tma_store_3d(&tmap_dq_t, stg, col0, prow, 0);
             tma_store_commit();
           }
         }
@@ -681,14 +733,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // arrays; delta comes from attn_delta_kernel, which evaluates it from the hi + lo context so that
     // its error stays far below the (dP - delta) cancellation it enters); the next item's values are
     // fetched during the current item's last iteration
-    auto load_nlse = [&](int item, int i) {
+    // index of this thread's query row of tile i of `item` in the [B, H, Sq] arrays, or -1
+    auto stat_index = [&](int item, int i) -> long long {
+      if (packed) {
+        const int h = item % p.H, g = item / p.H;
+        const long long grow = static_cast<long long>(g) * p.GS + r;   // global token row
+        if (i != 0 || r >= p.GS || grow >= static_cast<long long>(p.B) * p.Sq) return -1;
+        const long long bi = grow / p.Sq;
+        return (bi * p.H + h) * p.Sq + (grow - bi * p.Sq);
+      }
       const int qrow = i * 128 + r;
-      return (i < nq && qrow < p.Sq) ? -p.lse[static_cast<long long>(item) * p.Sq + qrow] * kLog2e : -INFINITY;
+      return (i < nq && qrow < p.Sq) ? static_cast<long long>(item) * p.Sq + qrow : -1;
+    };
+    auto load_nlse = [&](int item, int i) {
+      const long long idx = stat_index(item, i);
+      return idx >= 0 ? -p.lse[idx] * kLog2e : -INFINITY;
     };
     auto load_delta = [&](int item, int i) {
-      const int qrow = i * 128 + r;
-      return (i < nq && qrow < p.Sq) ? p.delta[static_cast<long long>(item) * p.Sq + qrow] : 0.f;
+      const long long idx = stat_index(item, i);
+      return idx >= 0 ? p.delta[idx] : 0.f;
     };
+    // packed: this thread's keys are those of its own image, [klo, khi); the warp's 32 rows touch the
+    // images between its first and last valid row, [wlo, whi) (warp-uniform: TMEM loads are collective)
+    int klo = 0, khi = 0, wlo = 0, whi = 0;
+    if (packed) {
+      const int w0 = (warp & 3) * 32;
+      if (r < p.GS) { klo = (r / p.Sq) * p.Sq; khi = klo + p.Sq; }
+      if (w0 < p.GS) {
+        const int wl = w0 + 31 < p.GS - 1 ? w0 + 31 : p.GS - 1;
+        wlo = (w0 / p.Sq) * p.Sq;
+        whi = (wl / p.Sq) * p.Sq + p.Sq;
+      }
+    }
     float nx0 = 0.f, nx1 = 0.f, nd0 = 0.f, nd1 = 0.f;
     if (blockIdx.x < items) {
       nx0 = load_nlse(blockIdx.x, 0); nx1 = load_nlse(blockIdx.x, 1);
@@ -721,16 +797,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // 8 keys: P = 2^(S * scale * log2e - lse * log2e), dS = P * (dP - delta), one 16-byte store each
         auto chunk_math = [&](const uint32_t (&sv)[8], const uint32_t (&dp)[8], int c, uint32_t (&pp)[4], uint32_t (&dd)[4]) {
           const int key0 = keyb + c * 8;
-          if (key0 < key_lim) {
-            const bool full = key0 + 8 <= key_lim;
+          const bool some = packed ? (key0 < khi && key0 + 8 > klo) : key0 < key_lim;
+          if (some) {
+            const bool full = packed ? (key0 >= klo && key0 + 8 <= khi) : key0 + 8 <= key_lim;
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
               float a0, a1;
               upk2(ffma2(pk2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2v, nlv), a0, a1);
               float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
               if (!full) {
-                p0 = (key0 + e < key_lim) ? p0 : 0.f;
-                p1 = (key0 + e + 1 < key_lim) ? p1 : 0.f;
+                if (packed) {
+                  p0 = static_cast<unsigned>(key0 + e - klo) < static_cast<unsigned>(khi - klo) ? p0 : 0.f;
+                  p1 = static_cast<unsigned>(key0 + e + 1 - klo) < static_cast<unsigned>(khi - klo) ? p1 : 0.f;
+                } else {
+                  p0 = (key0 + e < key_lim) ? p0 : 0.f;
+                  p1 = (key0 + e + 1 < key_lim) ? p1 : 0.f;
+                }
               }
               pp[e >> 1] = pack_bf16(p0, p1);
               float d0, d1;
@@ -755,10 +837,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           // coexist with pending results.
           uint32_t sv0[8], dp0[8], sv1[8], dp1[8], pp0[4], dd0[4], pp1[4], dd1[4];
           __syncwarp();
-          if (keyb < key_lim) {
+          if (packed ? (keyb < whi && keyb + 16 > wlo) : keyb < key_lim) {
             tmem_ld_32x8(ts, sv0);
             tmem_ld_32x8(td, dp0);
-            if (keyb + 8 < key_lim) {
+            if (packed || keyb + 8 < key_lim) {
               tmem_ld_32x8(ts + 8, sv1);
               tmem_ld_32x8(td + 8, dp1);
             }
@@ -784,10 +866,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           // MMA warp (next iteration's S / dP) with half of this iteration's exp math still to do
           uint32_t sv2[8], dp2[8], sv3[8], dp3[8], pp[4], dd[4];
           __syncwarp();
-          if (keyb + 16 < key_lim) {
+          if (packed ? (keyb + 16 < whi && keyb + 32 > wlo) : keyb + 16 < key_lim) {
             tmem_ld_32x8(ts + 16, sv2);
             tmem_ld_32x8(td + 16, dp2);
-            if (keyb + 24 < key_lim) {
+            if (packed || keyb + 24 < key_lim) {
               tmem_ld_32x8(ts + 24, sv3);
               tmem_ld_32x8(td + 24, dp3);
             }
@@ -1031,11 +1113,24 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo; p.lse = lse;
   p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk;
   p.kv_rows = (int)((Sk + 15) / 16 * 16); p.scale = scale;
+  // short self-attention sequences: G images per 128-row tile (VITSSL_ATTN_PACK=0 disables)
+  static const int pack_env = getenv("VITSSL_ATTN_PACK") ? atoi(getenv("VITSSL_ATTN_PACK")) : 1;
+  p.G = (pack_env != 0 && Sq == Sk && Sq <= 64 && B > 1) ? (int)(128 / Sq) : 1;
+  if (p.G > B) p.G = (int)B;
+  p.GS = p.G * (int)Sq;
   CUtensorMap mq, mk, mv;
   int rc;
-  if ((rc = make_head_map(&mq, q, p.B, p.Sq, p.H, ldq, 128))) return rc;
-  if ((rc = make_head_map(&mk, k, p.B, p.Sk, p.H, ldk, p.kv_rows))) return rc;
-  if ((rc = make_head_map(&mv, v, p.B, p.Sk, p.H, ldv, p.kv_rows))) return rc;
+  if (p.G > 1) {
+    p.kv_rows = (p.GS + 15) / 16 * 16;
+    // [B*S] token rows as ONE sequence: the tile of group g starts at row g*G*S
+    if ((rc = make_head_map(&mq, q, 1, p.B * p.Sq, p.H, ldq, 128))) return rc;
+    if ((rc = make_head_map(&mk, k, 1, p.B * p.Sk, p.H, ldk, p.kv_rows))) return rc;
+    if ((rc = make_head_map(&mv, v, 1, p.B * p.Sk, p.H, ldv, p.kv_rows))) return rc;
+  } else {
+    if ((rc = make_head_map(&mq, q, p.B, p.Sq, p.H, ldq, 128))) return rc;
+    if ((rc = make_head_map(&mk, k, p.B, p.Sk, p.H, ldk, p.kv_rows))) return rc;
+    if ((rc = make_head_map(&mv, v, p.B, p.Sk, p.H, ldv, p.kv_rows))) return rc;
+  }
   // the context (and its rounding residual) leave through 32 x 32 staging blocks + TMA stores when the
   // output rows are TMA-addressable (VITSSL_ATTN_FWD_STAGED=0 forces per-thread stores)
   static const int staged_env = getenv("VITSSL_ATTN_FWD_STAGED") ? atoi(getenv("VITSSL_ATTN_FWD_STAGED")) : 1;
@@ -1044,7 +1139,7 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
   memset(&molo, 0, sizeof(molo));
   // short sequences (S = 37: DINO local crops, cfg 1) keep per-thread stores: most of a 32-row block
   // would be clipped and the staging round trip costs more than it saves (58 vs 54 us at S = 37)
-  p.staged = (staged_env == 2 || (staged_env == 1 && Sq > 64)) ? 1 : 0;
+  p.staged = (p.G == 1 && (staged_env == 2 || (staged_env == 1 && Sq > 64))) ? 1 : 0;
   if (p.staged) {
     auto out_map = [&](CUtensorMap* m, void* base) {
       return make_tmap_bf16_3d_sw(m, base, (uint64_t)p.H * 64, (uint64_t)p.Sq, (uint64_t)p.B, (uint64_t)ldo * 2,
@@ -1055,18 +1150,22 @@ extern "C" int vitssl_attention_fwd(const void* q, const void* k, const void* v,
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
+    cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
     if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
+      err = cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES);
     if (err != cudaSuccess) { set_error("attention_fwd: smem attribute: %s", cudaGetErrorString(err)); return VITSSL_ERR_CUDA; }
     configured = true;
   }
-  const long long items = (long long)B * H * ((Sq + 127) / 128);
+  const long long items = (p.G > 1 ? (B + p.G - 1) / p.G : B) * H * ((Sq + 127) / 128);
   const long long slots = 2ll * num_sms();  // persistent: two CTAs per SM
   const unsigned grid = (unsigned)(items < slots ? items : slots);
-  cudaError_t lerr = p.staged
-      ? launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, mo, molo, p)
-      : launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, mo, molo, p);
+  cudaError_t lerr = p.G > 1
+      ? launch_pdl(attn_fwd_kernel<false, true>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, mo, molo, p)
+      : p.staged
+      ? launch_pdl(attn_fwd_kernel<true, false>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, mo, molo, p)
+      : launch_pdl(attn_fwd_kernel<false, false>, dim3(grid), dim3(FWD_THREADS), FWD_SMEM_BYTES, stream, mq, mk, mv, mo, molo, p);
   if (lerr != cudaSuccess) { set_error("attention_fwd: launch failed: %s", cudaGetErrorString(lerr)); return VITSSL_ERR_CUDA; }
   return check_launch("attention_fwd");
 }
@@ -1100,31 +1199,50 @@ extern "C" int vitssl_attention_bwd(const void* q, const void* k, const void* v,
     const int rc0 = check_launch("attention_delta");
     if (rc0) return rc0;
   }
+  // short self-attention sequences: G images per 128-row tile (VITSSL_ATTN_PACK=0 disables)
+  static const int pack_env = getenv("VITSSL_ATTN_PACK") ? atoi(getenv("VITSSL_ATTN_PACK")) : 1;
+  p.G = (pack_env != 0 && Sq == Sk && Sq <= 64 && B > 1) ? (int)(128 / Sq) : 1;
+  if (p.G > B) p.G = (int)B;
+  p.GS = p.G * (int)Sq;
+  const bool packed = p.G > 1;
+  // packed: the [B*S] token rows as one sequence (tile of group g = rows g*G*S ...)
+  const int mapB = packed ? 1 : p.B, mapSq = packed ? p.B * p.Sq : p.Sq, mapSk = packed ? p.B * p.Sk : p.Sk;
   CUtensorMap mq, mk, mv, mdo;
   int rc;
-  if ((rc = make_head_map(&mq, q, p.B, p.Sq, p.H, ldq, 128))) return rc;
-  if ((rc = make_head_map(&mk, k, p.B, p.Sk, p.H, ldk, 128))) return rc;
-  if ((rc = make_head_map(&mv, v, p.B, p.Sk, p.H, ldv, 128))) return rc;
-  if ((rc = make_head_map(&mdo, d_out, p.B, p.Sq, p.H, ldo, 128))) return rc;
-  // outputs leave through 32-column x 32-row staging blocks (64-byte swizzle), clipped at S
-  CUtensorMap mdq, mdk, mdv;
-  auto out_map = [&](CUtensorMap* m, void* base, int S, long long ld) {
-    return make_tmap_bf16_3d_sw(m, base, (uint64_t)p.H * 64, (uint64_t)S, (uint64_t)p.B, (uint64_t)ld * 2,
-                                (uint64_t)S * ld * 2, 32, 32, 1, 64);
+  if ((rc = make_head_map(&mq, q, mapB, mapSq, p.H, ldq, 128))) return rc;
+  if ((rc = make_head_map(&mk, k, mapB, mapSk, p.H, ldk, 128))) return rc;
+  if ((rc = make_head_map(&mv, v, mapB, mapSk, p.H, ldv, 128))) return rc;
+  if ((rc = make_head_map(&mdo, d_out, mapB, mapSq, p.H, ldo, 128))) return rc;
+  // outputs leave through 32-column x 32-row staging blocks (64-byte swizzle), clipped at S; packed:
+  // clipped at the end of the [B*S] rows, and the block that straddles G*S uses a map with fewer rows
+  CUtensorMap mdq, mdk, mdv, mdq_t, mdk_t, mdv_t;
+  auto out_map = [&](CUtensorMap* m, void* base, int S, long long ld, int box_rows) {
+    return make_tmap_bf16_3d_sw(m, base, (uint64_t)p.H * 64, (uint64_t)S, (uint64_t)mapB, (uint64_t)ld * 2,
+                                (uint64_t)S * ld * 2, 32, (uint32_t)box_rows, 1, 64);
   };
-  if ((rc = out_map(&mdq, dq, p.Sq, lddq))) return rc;
-  if ((rc = out_map(&mdk, dk, p.Sk, lddk))) return rc;
-  if ((rc = out_map(&mdv, dv, p.Sk, lddv))) return rc;
+  if ((rc = out_map(&mdq, dq, mapSq, lddq, 32))) return rc;
+  if ((rc = out_map(&mdk, dk, mapSk, lddk, 32))) return rc;
+  if ((rc = out_map(&mdv, dv, mapSk, lddv, 32))) return rc;
+  const int tail_rows = (packed && p.GS % 32) ? p.GS % 32 : 32;
+  if ((rc = out_map(&mdq_t, dq, mapSq, lddq, tail_rows))) return rc;
+  if ((rc = out_map(&mdk_t, dk, mapSk, lddk, tail_rows))) return rc;
+  if ((rc = out_map(&mdv_t, dv, mapSk, lddv, tail_rows))) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
+    cudaError_t err = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
     if (err != cudaSuccess) { set_error("attention_bwd: smem attribute: %s", cudaGetErrorString(err)); return VITSSL_ERR_CUDA; }
     configured = true;
   }
-  const long long items = (long long)B * H;  // persistent: one CTA per SM walks the (batch, head) items
+  // persistent: one CTA per SM walks the (batch, head) items — packed: (group of G images, head)
+  const long long items = (packed ? (B + p.G - 1) / p.G : B) * H;
   const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
-  cudaError_t lerr = launch_pdl(attn_bwd_kernel, dim3(grid), dim3(BWD_THREADS), BWD_SMEM_BYTES, stream, mq, mk, mv, mdo,
-                                mdq, mdk, mdv, p);
+  cudaError_t lerr = packed
+      ? launch_pdl(attn_bwd_kernel<true>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM_BYTES, stream, mq, mk, mv, mdo, mdq, mdk,
+                   mdv, mdq_t, mdk_t, mdv_t, p)
+      : launch_pdl(attn_bwd_kernel<false>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM_BYTES, stream, mq, mk, mv, mdo, mdq, mdk,
+                   mdv, mdq_t, mdk_t, mdv_t, p);
   if (lerr != cudaSuccess) { set_error("attention_bwd: launch failed: %s", cudaGetErrorString(lerr)); return VITSSL_ERR_CUDA; }
   return check_launch("attention_bwd");
 }
