@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "vit-ssl_b200"))
 import torch
 from vit_core._backend import ops, lib
-B, S, H, D = 256, int(os.environ.get("S", 196)), 6, 384
+B, S, H, D = int(os.environ.get("B", 256)), int(os.environ.get("S", 196)), 6, 384
 bf = torch.bfloat16
 qkv = (torch.randn(B, S, 3 * D, device="cuda") * 0.5).to(bf)
 dctx = (torch.randn(B, S, D, device="cuda") * 0.5).to(bf)
