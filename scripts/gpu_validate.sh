@@ -14,3 +14,4 @@ print("$f", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms
 P
 done
 tail -c 400 gpurun_out/final_bench_reference_arm.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
