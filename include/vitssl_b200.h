@@ -125,7 +125,10 @@ int vitssl_add_layernorm_bwd_acc(const void* dy, const float* x, int64_t ldx, co
  * delta = rowsum(O * dO) is evaluated from out + out_lo (16 significant bits) because its rounding
  * error enters dS = P (dP - delta) coherently along a row and, on real activations, dominated the
  * error of dQ when taken from the bf16 context alone. `delta` is a caller-provided fp32 [B,H,Sq]
- * workspace that vitssl_attention_bwd fills itself (one extra HBM-bound launch). */
+ * workspace that vitssl_attention_bwd fills itself (one extra HBM-bound launch).
+ * Self-attention with Sq == Sk <= 64 (DINO local crops, cfg 1) runs with floor(128 / S) images per
+ * 128-row tile and block-diagonal masking; this needs the images' token rows to be contiguous
+ * (row b*S + s at pitch ld*, which is what every caller passes) and changes no result. */
 int vitssl_attention_supported(int64_t Sq, int64_t Sk, int64_t d_head);
 int vitssl_attention_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
                          int64_t ldv, void* out, void* out_lo, int64_t ldo, float* lse, int64_t B,
