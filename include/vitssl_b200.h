@@ -200,6 +200,12 @@ typedef struct {
   int64_t l_begin, l_end;
 } vitssl_encoder_bwd_args;
 int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* args, vitssl_stream_t stream);
+/* Both stack calls replay a CUDA graph of their own launch sequence when they are called again with
+ * identical arguments (every scalar and pointer; the dropout seed is exempt: it travels through a
+ * device word) — the steady state of a training loop. A call whose arguments were not seen before
+ * takes the direct path, so results never depend on the cache; VITSSL_GRAPH=0 disables it. Counters
+ * for tests and bench.py: graphs captured / calls served by a replay since the library was loaded. */
+int vitssl_graph_stats(int64_t* captured, int64_t* replayed);
 
 /* ---- weight casts, EMA, bias gradients (host_* arguments are HOST arrays of device pointers) */
 /* fp32 -> bf16 for `count` tensors in one or a few launches (parameters stay fp32 nn.Parameters;

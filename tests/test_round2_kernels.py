@@ -1,6 +1,8 @@
 """GPU tests of the round-2 additions: fused AdamW (+GradScaler hand-over, bf16 shadows), EMA with
 shadows, uint8 image kernels, bicubic positional-embedding kernel, multi-pass encoder-stack node,
 nn.L1Loss dispatch, the C-side launch profile, shape validation and DINO-loss generality."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -9,6 +11,7 @@ from oracle import vit_ref
 from parity_utils import rel, rel_l2
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 # ------------------------------------------------------------------------------------------
@@ -444,3 +447,64 @@ def test_simmim_and_dino_losses_are_prefetched():
     s = torch.randn(4, 4, 512, device="cuda", requires_grad=True)
     dl = DINOLoss(0.04, 0.1)(t, s, torch.zeros(512, device="cuda"))
     assert isinstance(dl, PrefetchedScalar) and dl.item() == torch.Tensor.item(dl)
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA-graph replay of the C-sequenced stack (csrc/encoder.cu): same bits as the direct path
+# ------------------------------------------------------------------------------------------
+_GRAPH_SCRIPT = r"""
+import json, os, sys
+sys.path.insert(0, os.path.join(os.environ["VITSSL_ROOT"], "vit-ssl_b200"))
+import torch
+from torch import nn
+from vit_core import EncoderBlock
+from vit_core._backend import functional as Fb, lib
+torch.manual_seed(0)
+blocks = nn.ModuleList([EncoderBlock(128, 2, 256, 0.1) for _ in range(3)]).cuda().train()
+params = [p for p in blocks.parameters()]
+x = torch.randn(64, 64, 128, device="cuda", requires_grad=True)      # 4096 token rows
+w = torch.randn(64, 64, 128, device="cuda")
+out = []
+for step in range(8):
+    torch.manual_seed(100 + step)               # the dropout seed of the step is drawn from this stream
+    for p in params + [x]:
+        p.grad = None
+    y, _ = Fb.encoder_stack(blocks, x)
+    (y * w).sum().backward()
+    g = [(float(p.grad.double().sum()), float(p.grad.double().abs().sum())) for p in params]
+    out.append((float(y.double().sum()).hex(), float(y.double().abs().sum()).hex(), float(x.grad.double().abs().sum()).hex(), g))
+    with torch.no_grad():                      # weights move (by the same amounts in both runs): shadows are re-cast
+        gen = torch.Generator(device="cuda").manual_seed(7 + step)
+        for p in params:
+            p.add_(torch.randn(p.shape, device="cuda", generator=gen), alpha=1e-3)
+print(json.dumps({"steps": out, "graphs": lib.graph_stats()}))
+"""
+
+
+def _run_graph_script(graph):
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, VITSSL_GRAPH=str(graph), VITSSL_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-c", _GRAPH_SCRIPT], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_stack_graph_replay_is_bit_identical_to_direct_launches():
+    """Eight forward + backward passes of a 3-block stack with dropout 0.1 (fresh seed every step, weights
+    moving): with the graph cache the later steps are replays of a captured launch sequence whose only
+    per-step input, the dropout seed, travels through a device word. Outputs and every gradient must
+    equal the direct path's bit for bit."""
+    direct = _run_graph_script(0)
+    replay = _run_graph_script(1)
+    assert direct["graphs"] == [0, 0]
+    captured, replayed = replay["graphs"]
+    assert captured >= 2 and replayed >= 6, replay["graphs"]       # forward and backward graphs, reused
+    for a, b in zip(replay["steps"], direct["steps"]):
+        # outputs and the input gradient: bit for bit. Parameter gradients are accumulated with split-K
+        # reduce-adds / atomics whose order differs from run to run (with or without graphs)
+        assert a[:3] == b[:3]
+        for (ga, na), (gb, nb) in zip(a[3], b[3]):
+            assert abs(ga - gb) <= 1e-5 * nb and abs(na - nb) <= 1e-5 * nb, (ga, gb, na, nb)
+    assert len({s[0] for s in direct["steps"]}) == 8              # different seeds / weights every step

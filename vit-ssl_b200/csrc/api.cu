@@ -27,6 +27,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+long long launches_now() { return g_launches.load(); }
+void add_launches(long long n) { g_launches += n; }
+
 int check_launch(const char* what) {
   ++g_launches;
   cudaError_t err = cudaGetLastError();

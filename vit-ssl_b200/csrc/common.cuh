@@ -53,6 +53,12 @@ struct ProfScope {
   int idx_;
   cudaStream_t stream_;
 };
+// non-null while encoder.cu captures a stack call into a CUDA graph: dropout kernels launched by this
+// thread then read their seed from that device word instead of their by-value argument
+const unsigned long long* seed_slot_override();
+// kernels a replayed graph launches are counted like individually launched ones (vitssl_launch_count)
+long long launches_now();
+void add_launches(long long n);
 bool pdl_enabled();  // programmatic dependent launch for the hot kernels (VITSSL_PDL=0 disables)
 
 // Launch with programmatic stream serialization: the grid may begin (prologue: barrier init,
@@ -152,23 +158,27 @@ constexpr int DROPOUT_PHILOX_ROUNDS = 7;
 // Same generator with the round keys precomputed on the host: as kernel parameters they become
 // constant-bank operands of the round's 3-input XOR, so a round is 2 IMAD.WIDE + 2 LOP3 and no
 // key arithmetic (the in-kernel schedule costs two more ALU instructions per round and draw).
+// The KEY is the dropout site (`offset`, the same every step, so the round keys are launch constants
+// that a replayed CUDA graph may keep) and the per-step `seed` rides in the two high counter words,
+// which a kernel can take from its arguments or from a device word: a counter-based generator is a
+// keyed bijection of the whole 128-bit counter, so (site, seed, index) -> draw is as good either way.
 struct PhiloxKeys7 {
   uint32_t k[2 * DROPOUT_PHILOX_ROUNDS];  // (k0, k1) of round r at [2r], [2r+1]
-  uint32_t c2, c3;                        // offset words
+  uint32_t c2, c3;                        // seed words
 };
 inline PhiloxKeys7 make_philox_keys7(uint64_t seed, uint64_t offset) {
   PhiloxKeys7 pk;
-  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const uint64_t key = offset * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;  // spread the small site index
+  uint32_t k0 = static_cast<uint32_t>(key), k1 = static_cast<uint32_t>(key >> 32);
   for (int r = 0; r < DROPOUT_PHILOX_ROUNDS; ++r) {
     pk.k[2 * r] = k0; pk.k[2 * r + 1] = k1;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  pk.c2 = static_cast<uint32_t>(offset); pk.c3 = static_cast<uint32_t>(offset >> 32);
+  pk.c2 = static_cast<uint32_t>(seed); pk.c3 = static_cast<uint32_t>(seed >> 32);
   return pk;
 }
-__device__ __forceinline__ uint4 philox4x32_7_keyed(const PhiloxKeys7& pk, uint64_t index) {
+__device__ __forceinline__ uint4 philox4x32_7_keyed(const PhiloxKeys7& pk, uint32_t c2, uint32_t c3, uint64_t index) {
   uint32_t c0 = static_cast<uint32_t>(index), c1 = static_cast<uint32_t>(index >> 32);
-  uint32_t c2 = pk.c2, c3 = pk.c3;
 #pragma unroll
   for (int r = 0; r < DROPOUT_PHILOX_ROUNDS; ++r) {
     uint32_t hi0, lo0, hi1, lo1;

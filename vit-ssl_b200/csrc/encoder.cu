@@ -40,7 +40,7 @@ inline double attn_flops(int64_t B, int64_t H, int64_t S) { return 4.0 * (double
     VITSSL_TRY(call);                         \
   } while (0)
 
-extern "C" int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* a, cudaStream_t stream) {
+static int stack_fwd_body(const vitssl_encoder_fwd_args* a, cudaStream_t stream) {
   VITSSL_REQUIRE(a != nullptr && a->L >= 1, VITSSL_ERR_ARG, "encoder_stack_fwd: bad args");
   const int64_t B = a->B, S = a->S, D = a->D, H = a->H, F = a->F, L = a->L;
   const int64_t M = B * S;
@@ -93,7 +93,7 @@ extern "C" int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* a, cudaSt
   return 0;
 }
 
-extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaStream_t stream) {
+static int stack_bwd_body(const vitssl_encoder_bwd_args* a, cudaStream_t stream) {
   VITSSL_REQUIRE(a != nullptr && a->fwd != nullptr && a->fwd->L >= 1 && a->delta != nullptr, VITSSL_ERR_ARG,
                  "encoder_stack_bwd: bad args");
   const vitssl_encoder_fwd_args* f = a->fwd;
@@ -175,5 +175,193 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
                                               f->seed, (uint64_t)(l > 0 ? 3 * l - 1 : 0), stream));
     gs = gs_in;
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA-graph replay of a stack call. The ~100 (forward) / ~150 (backward) launches of a stack are
+// the same every step when the caller's buffers sit at the same addresses (the steady state of a
+// caching allocator in a training loop); between dependent launches in a stream the GPU idles 2-3.5 us
+// (profiles/r2_gaps.md: 0.53 ms of a 14.7 ms SimMIM step, 1.3 ms of a DINO step), a graph replay of
+// the same kernels does not (scripts/micro/graph_gap.py: -2.0 us per launch). A call is keyed on
+// every scalar and pointer it hands over; the second call with a known key is captured
+// (cudaStreamBeginCapture around the very same sequencing code) and instantiated, later ones are
+// one cudaGraphLaunch. The only per-step value, the dropout seed, travels through a device word
+// that the dropout kernels read (layernorm.cu / gemm_sm100.cu: seed_slot_override) and that a
+// one-thread kernel sets ahead of the replay, in stream order. A key that misses takes the direct
+// path, so results never depend on the cache. VITSSL_GRAPH=0 disables; profiling bypasses it.
+// ------------------------------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+
+namespace {
+__device__ unsigned long long g_seed_word;
+__global__ void set_seed_kernel(unsigned long long s) { g_seed_word = s; }
+
+struct GraphEntry {
+  std::vector<unsigned char> key;
+  cudaGraphExec_t exec = nullptr;
+  int seen = 0;
+  long long launches = 0;  // kernels and memsets the captured sequence holds
+  bool bad = false;  // capture or instantiation failed once: stay on the direct path
+  unsigned long long stamp = 0;
+};
+std::mutex g_graph_mu;
+std::vector<GraphEntry> g_graphs;
+unsigned long long g_graph_stamp = 0;
+long long g_graph_captured = 0, g_graph_replayed = 0;
+constexpr size_t GRAPH_CACHE_ENTRIES = 24;
+thread_local const unsigned long long* tl_seed_slot = nullptr;
+
+bool graphs_enabled() {
+  static const bool on = !(getenv("VITSSL_GRAPH") && atoi(getenv("VITSSL_GRAPH")) == 0);
+  return on;
+}
+const unsigned long long* seed_word_address() {
+  static const unsigned long long* addr = [] {
+    void* p = nullptr;
+    return cudaGetSymbolAddress(&p, g_seed_word) == cudaSuccess ? static_cast<const unsigned long long*>(p) : nullptr;
+  }();
+  return addr;
+}
+template <typename T>
+void key_put(std::vector<unsigned char>& k, const T& v) {
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&v);
+  k.insert(k.end(), b, b + sizeof(T));
+}
+template <typename P>
+void key_put_array(std::vector<unsigned char>& k, P const* arr, int64_t L) {
+  if (arr == nullptr) { key_put(k, (void*)nullptr); return; }
+  for (int64_t l = 0; l < L; ++l) key_put(k, arr[l]);
+}
+void key_fwd(std::vector<unsigned char>& k, const vitssl_encoder_fwd_args* a) {
+  key_put(k, a->B); key_put(k, a->S); key_put(k, a->D); key_put(k, a->H); key_put(k, a->F); key_put(k, a->L);
+  key_put(k, a->dropout_p); key_put(k, a->eps);
+  key_put(k, a->x_in); key_put(k, a->out); key_put(k, a->y1); key_put(k, a->y2[0]); key_put(k, a->y2[1]);
+  const int64_t L = a->L;
+  key_put_array(k, a->wqkv, L); key_put_array(k, a->wo, L); key_put_array(k, a->w1, L); key_put_array(k, a->w2, L);
+  key_put_array(k, a->b1, L); key_put_array(k, a->b2, L); key_put_array(k, a->g1, L); key_put_array(k, a->be1, L);
+  key_put_array(k, a->g2, L); key_put_array(k, a->be2, L); key_put_array(k, a->xs, L); key_put_array(k, a->mean1, L);
+  key_put_array(k, a->rstd1, L); key_put_array(k, a->xn1, L); key_put_array(k, a->qkv, L); key_put_array(k, a->ctx, L);
+  key_put_array(k, a->lse, L); key_put_array(k, a->ctx_lo, L); key_put_array(k, a->xmid, L); key_put_array(k, a->mean2, L);
+  key_put_array(k, a->rstd2, L); key_put_array(k, a->xn2, L); key_put_array(k, a->u, L); key_put_array(k, a->h, L);
+}
+void key_bwd(std::vector<unsigned char>& k, const vitssl_encoder_bwd_args* a) {
+  key_fwd(k, a->fwd);
+  key_put(k, a->gout); key_put(k, a->dx); key_put(k, a->dbranch); key_put(k, a->du); key_put(k, a->dxn); key_put(k, a->dctx);
+  key_put(k, a->dqkv); key_put(k, a->delta); key_put(k, a->gs[0]); key_put(k, a->gs[1]);
+  const int64_t L = a->fwd->L;
+  key_put_array(k, a->dwqkv, L); key_put_array(k, a->dwo, L); key_put_array(k, a->dw1, L); key_put_array(k, a->db1, L);
+  key_put_array(k, a->dw2, L); key_put_array(k, a->db2, L); key_put_array(k, a->dg1, L); key_put_array(k, a->dbe1, L);
+  key_put_array(k, a->dg2, L); key_put_array(k, a->dbe2, L);
+  key_put(k, a->l_begin); key_put(k, a->l_end);
+}
+
+// run `body` (which sequences the launches on `stream`) directly, or as a captured / replayed graph
+template <typename Body>
+int graph_dispatch(std::vector<unsigned char>& key, unsigned long long seed, bool uses_seed, cudaStream_t stream, Body&& body) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const unsigned long long* slot = seed_word_address();
+  if (!graphs_enabled() || prof_on() || slot == nullptr || cudaStreamIsCapturing(stream, &cs) != cudaSuccess ||
+      cs != cudaStreamCaptureStatusNone)
+    return body(stream);
+  // the sequence is captured on a stream of our own (the caller's may be the legacy default stream,
+  // which cannot be captured) and the instantiated graph is launched on the caller's stream
+  static cudaStream_t cap_stream = [] {
+    cudaStream_t st = nullptr;
+    return cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess ? st : nullptr;
+  }();
+  if (cap_stream == nullptr) return body(stream);
+  std::unique_lock<std::mutex> lock(g_graph_mu);
+  GraphEntry* e = nullptr;
+  for (auto& g : g_graphs)
+    if (g.key == key) { e = &g; break; }
+  if (e == nullptr) {
+    if (g_graphs.size() >= GRAPH_CACHE_ENTRIES) {  // evict the least recently used entry
+      size_t victim = 0;
+      for (size_t i = 1; i < g_graphs.size(); ++i)
+        if (g_graphs[i].stamp < g_graphs[victim].stamp) victim = i;
+      if (g_graphs[victim].exec) cudaGraphExecDestroy(g_graphs[victim].exec);
+      g_graphs.erase(g_graphs.begin() + victim);
+    }
+    g_graphs.emplace_back();
+    e = &g_graphs.back();
+    e->key = key;
+  }
+  e->stamp = ++g_graph_stamp;
+  e->seen += 1;
+  if (e->bad || e->seen < 2) {  // first sighting (one-off shapes never pay for a capture) or known failure
+    lock.unlock();
+    return body(stream);
+  }
+  if (e->exec == nullptr) {
+    // capture the same sequencing code; the dropout kernels read the seed word instead of their argument
+    if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      e->bad = true;
+      cudaGetLastError();
+      lock.unlock();
+      return body(stream);
+    }
+    tl_seed_slot = slot;
+    const long long n0 = launches_now();
+    const int rc = body(cap_stream);
+    e->launches = launches_now() - n0;
+    add_launches(-e->launches);  // counted below, once per replay
+    tl_seed_slot = nullptr;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+    if (rc != 0 || ce != cudaSuccess || graph == nullptr ||
+        cudaGraphInstantiate(&e->exec, graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      e->exec = nullptr;
+      e->bad = true;
+      cudaGetLastError();
+      lock.unlock();
+      return rc != 0 ? rc : body(stream);  // nothing was launched by the capture: run it for real
+    }
+    cudaGraphDestroy(graph);
+    g_graph_captured += 1;
+  }
+  cudaGraphExec_t exec = e->exec;
+  g_graph_replayed += 1;
+  add_launches(e->launches);
+  if (uses_seed) set_seed_kernel<<<1, 1, 0, stream>>>(seed);
+  const cudaError_t le = cudaGraphLaunch(exec, stream);
+  lock.unlock();
+  if (le != cudaSuccess) {
+    set_error("encoder_stack: graph launch failed: %s", cudaGetErrorString(le));
+    return VITSSL_ERR_CUDA;
+  }
+  return check_launch("encoder_stack_graph");
+}
+}  // namespace
+
+namespace vitssl {
+const unsigned long long* seed_slot_override() { return tl_seed_slot; }
+}  // namespace vitssl
+
+extern "C" int vitssl_encoder_stack_fwd(const vitssl_encoder_fwd_args* a, cudaStream_t stream) {
+  if (a == nullptr || a->L < 1) return stack_fwd_body(a, stream);
+  std::vector<unsigned char> key;
+  key.reserve(4096);
+  key_put(key, 'F');
+  key_fwd(key, a);
+  return graph_dispatch(key, a->seed, a->dropout_p > 0.f, stream, [&](cudaStream_t st) { return stack_fwd_body(a, st); });
+}
+
+extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaStream_t stream) {
+  if (a == nullptr || a->fwd == nullptr || a->fwd->L < 1) return stack_bwd_body(a, stream);
+  std::vector<unsigned char> key;
+  key.reserve(4096);
+  key_put(key, 'B');
+  key_bwd(key, a);
+  return graph_dispatch(key, a->fwd->seed, a->fwd->dropout_p > 0.f, stream,
+                        [&](cudaStream_t st) { return stack_bwd_body(a, st); });
+}
+
+extern "C" int vitssl_graph_stats(int64_t* captured, int64_t* replayed) {
+  std::lock_guard<std::mutex> lock(g_graph_mu);
+  if (captured) *captured = g_graph_captured;
+  if (replayed) *replayed = g_graph_replayed;
   return 0;
 }

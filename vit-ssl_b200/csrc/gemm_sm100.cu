@@ -57,7 +57,8 @@ struct GemmEpi {
   int tma_out;   // 1: epilogue goes through staging + TMA store (tmap_c / tmap_aux valid)
   uint32_t drop_th2;  // (p * 32768) * 0x10001, 0 = no dropout (common.cuh: dropout_lane_mask2)
   float drop_scale;
-  PhiloxKeys7 keys;  // dropout generator state: (seed, offset) expanded to round keys on the host
+  PhiloxKeys7 keys;  // dropout generator state: site round keys (host-expanded) + the seed words
+  const unsigned long long* seed_slot;  // non-null: the seed words come from this device word (graph replay)
   float* a_colsum;   // nullable: a_colsum[m] += alpha * sum_k op(A)[m, k] (bias gradient fused into a wgrad)
 };
 constexpr int ONES_OFFSET = 512;  // all-ones bf16 block (512 B) inside the 1 KB barrier page
@@ -176,11 +177,17 @@ __device__ __forceinline__ void epilogue_math_bf16(const uint32_t (&v)[32], uint
     const f32x2 scv = MODE == VITSSL_EPI_DGELU ? pk2(sc * e.alpha, sc * e.alpha) : pk2(sc, sc);
     const unsigned long long g8 =
         (static_cast<unsigned long long>(row) * s.N + nb) >> 3;  // N % 8 == 0 enforced when dropping
+    uint32_t sd2 = e.keys.c2, sd3 = e.keys.c3;
+    if (drop && e.seed_slot != nullptr) {
+      const unsigned long long sv = __ldg(e.seed_slot);
+      sd2 = static_cast<uint32_t>(sv);
+      sd3 = static_cast<uint32_t>(sv >> 32);
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       uint32_t keep[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
       if (drop) {
-        const uint4 r = philox4x32_7_keyed(e.keys, g8 + g);
+        const uint4 r = philox4x32_7_keyed(e.keys, sd2, sd3, g8 + g);
         keep[0] = dropout_lane_mask2(r.x, e.drop_th2);
         keep[1] = dropout_lane_mask2(r.y, e.drop_th2);
         keep[2] = dropout_lane_mask2(r.z, e.drop_th2);
@@ -884,6 +891,7 @@ static int gemm_impl(const void* A, const void* B, void* C, int64_t M, int64_t N
   e.drop_th2 = static_cast<uint32_t>(dropout_p * 32768.0f) * 0x10001u;
   e.drop_scale = 1.0f / (1.0f - dropout_p);
   e.keys = make_philox_keys7(philox_seed, philox_offset);
+  e.seed_slot = dropout_p > 0.f ? seed_slot_override() : nullptr;
   e.a_colsum = a_colsum;
 
   // TMA needs 16-byte aligned bases and row pitches

@@ -29,6 +29,7 @@ struct LnFwdArgs {
   float* mean; float* rstd;                // [rows]
   long long rows; int D; float eps;
   uint32_t drop_thresh16; float drop_scale; unsigned long long seed, offset;
+  const unsigned long long* seed_slot;  // non-null: the seed is read from this device word (graph replay, encoder.cu)
 };
 
 struct LnBwdArgs {
@@ -41,7 +42,14 @@ struct LnBwdArgs {
   float* dgamma; float* dbeta;  // [D], pre-zeroed, accumulated with atomics
   long long rows; int D;
   uint32_t drop_thresh16; float drop_scale; unsigned long long seed, offset;
+  const unsigned long long* seed_slot;  // non-null: the seed is read from this device word (graph replay, encoder.cu)
 };
+
+// dropout seed of a launch: its argument, or the device word a replayed CUDA graph points at
+template <typename Args>
+__device__ __forceinline__ unsigned long long eff_seed(const Args& a) {
+  return a.seed_slot != nullptr ? __ldg(a.seed_slot) : a.seed;
+}
 
 // 8 consecutive elements of a row as four packed fp32 pairs (FFMA2 / FADD2 / FMUL2 operate on both)
 struct Vec8 {
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnFwdArgs a
       if (a.branch) {
         const Vec8 bf = load8_bf16(a.branch + row * a.D + c);
         if (a.drop_thresh16) {
-          const Vec8 m = dropout_mult8(a.seed, a.offset, static_cast<unsigned long long>(row * a.D + c) >> 3,
+          const Vec8 m = dropout_mult8(eff_seed(a), a.offset, static_cast<unsigned long long>(row * a.D + c) >> 3,
                                        a.drop_thresh16, a.drop_scale);
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[g].p[i] = ffma2(bf.p[i], m.p[i], v[g].p[i]);
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd4_kernel(const LnFwdArgs 
         const int c = (g * 32 + lane) * 4;
         const Vec4 bf = unpack4_bf16(braw[g]);
         if (a.drop_thresh16) {
-          const Vec4 m = dropout_mult4(a.seed, a.offset, static_cast<unsigned long long>(row * a.D + c),
+          const Vec4 m = dropout_mult4(eff_seed(a), a.offset, static_cast<unsigned long long>(row * a.D + c),
                                        a.drop_thresh16, a.drop_scale);
           v[g].p[0] = ffma2(bf.p[0], m.p[0], v[g].p[0]);
           v[g].p[1] = ffma2(bf.p[1], m.p[1], v[g].p[1]);
@@ -395,7 +403,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, bwd4_ctas_per_sm(NG4)) ln_bwd4_
       if (a.dx) store4_f32(a.dx + row * a.ld_dx + c, o);
       if (a.dbranch) {
         if (a.drop_thresh16) {
-          const Vec4 m = dropout_mult4(a.seed, a.offset, static_cast<unsigned long long>(row * a.D + c),
+          const Vec4 m = dropout_mult4(eff_seed(a), a.offset, static_cast<unsigned long long>(row * a.D + c),
                                        a.drop_thresh16, a.drop_scale);
           o.p[0] = fmul2(o.p[0], m.p[0]);
           o.p[1] = fmul2(o.p[1], m.p[1]);
@@ -429,7 +437,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_generic_kernel(const LnF
       float b = __bfloat162float(a.branch[row * a.D + c]);
       if (a.drop_thresh16) {
         const unsigned long long e = static_cast<unsigned long long>(row * a.D + c);
-        const uint32_t keep = dropout_keep8(a.seed, a.offset, e >> 3, a.drop_thresh16);
+        const uint32_t keep = dropout_keep8(eff_seed(a), a.offset, e >> 3, a.drop_thresh16);
         b = ((keep >> (e & 7)) & 1u) ? b * a.drop_scale : 0.f;
       }
       a.x_out[row * a.D + c] = xr[c] + b;
@@ -513,7 +521,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NG <= 2 ? 4 : 2) ln_bwd_kernel(
         if (a.dx) store8_f32(a.dx + row * a.ld_dx + c, o);
         if (a.dbranch) {
           if (a.drop_thresh16) {
-            const Vec8 m = dropout_mult8(a.seed, a.offset, static_cast<unsigned long long>(row * a.D + c) >> 3,
+            const Vec8 m = dropout_mult8(eff_seed(a), a.offset, static_cast<unsigned long long>(row * a.D + c) >> 3,
                                          a.drop_thresh16, a.drop_scale);
 #pragma unroll
             for (int i = 0; i < 4; ++i) o.p[i] = fmul2(o.p[i], m.p[i]);
@@ -574,7 +582,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_generic_kernel(const LnB
       if (a.dbranch) {
         if (a.drop_thresh16) {
           const unsigned long long e = static_cast<unsigned long long>(row * a.D + c);
-          const uint32_t keep = dropout_keep8(a.seed, a.offset, e >> 3, a.drop_thresh16);
+          const uint32_t keep = dropout_keep8(eff_seed(a), a.offset, e >> 3, a.drop_thresh16);
           o = ((keep >> (e & 7)) & 1u) ? o * a.drop_scale : 0.f;
         }
         a.dbranch[row * a.D + c] = __float2bfloat16_rn(o);
@@ -609,7 +617,7 @@ extern "C" int vitssl_add_layernorm_fwd(const float* x, int64_t ldx, const void*
   a.x_out = x_out; a.gamma = gamma; a.beta = beta; a.y = reinterpret_cast<__nv_bfloat16*>(y);
   a.mean = mean; a.rstd = rstd; a.rows = rows; a.D = (int)D; a.eps = eps;
   a.drop_thresh16 = static_cast<uint32_t>(dropout_p * 65536.0f);
-  a.drop_scale = 1.0f / (1.0f - dropout_p); a.seed = philox_seed; a.offset = philox_offset;
+  a.drop_scale = 1.0f / (1.0f - dropout_p); a.seed = philox_seed; a.offset = philox_offset; a.seed_slot = seed_slot_override();
   const long long want_f = (rows + LN_WARPS - 1) / LN_WARPS;
   // one warp per row, no grid cap: measured faster than a capped grid-stride launch (44 vs 53 us
   // for 50176 x 384) — the row loop only matters beyond 2^31 / 4 rows
@@ -677,7 +685,7 @@ extern "C" int vitssl_add_layernorm_bwd_acc(const void* dy, const float* x, int6
   a.dbranch = reinterpret_cast<__nv_bfloat16*>(dbranch); a.dgamma = dgamma; a.dbeta = dbeta;
   a.rows = rows; a.D = (int)D;
   a.drop_thresh16 = static_cast<uint32_t>(dropout_p * 65536.0f);
-  a.drop_scale = 1.0f / (1.0f - dropout_p); a.seed = philox_seed; a.offset = philox_offset;
+  a.drop_scale = 1.0f / (1.0f - dropout_p); a.seed = philox_seed; a.offset = philox_offset; a.seed_slot = seed_slot_override();
   long long want = (rows + LN_WARPS - 1) / LN_WARPS;
   static const int impl = getenv("VITSSL_LN_IMPL") ? atoi(getenv("VITSSL_LN_IMPL")) : 1;  // 0: 8-per-lane kernels only
   const int ng4 = (int)(D / 128);

@@ -67,6 +67,7 @@ SIGNATURES["vitssl_interp_rows_bwd"] = "pppp" + "llll" + "s"
 SIGNATURES["vitssl_l1_loss_bwd"] = "pppl" + "s"
 SIGNATURES["vitssl_adamw_step"] = "ppppppp" + "i" + "fffff" + "pp" + "s"
 SIGNATURES["vitssl_profile_read"] = "lplpp"
+SIGNATURES["vitssl_graph_stats"] = "pp"
 SIGNATURES["vitssl_multi_ema_shadow"] = "ppppifs"
 SIGNATURES["vitssl_mean_tokens_f32"] = "pp" + "lll" + "s"
 SIGNATURES["vitssl_knn_cosine"] = "pppppppp" + "lllll" + "s"
@@ -165,6 +166,13 @@ def profile_collect():
         call("vitssl_profile_read", i, ctypes.addressof(kind), 64, ctypes.addressof(work), ctypes.addressof(ms))
         out.append((kind.value.decode(), float(ms.value), float(work.value)))
     return out
+
+
+def graph_stats():
+    """(graphs captured, stack calls served by a graph replay) since the library was loaded (csrc/encoder.cu)."""
+    c, r = ctypes.c_int64(), ctypes.c_int64()
+    call("vitssl_graph_stats", ctypes.addressof(c), ctypes.addressof(r))
+    return int(c.value), int(r.value)
 
 
 def launch_count(reset: bool = False) -> int:
