@@ -206,6 +206,10 @@ int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* args, vitssl_stream_
  * takes the direct path, so results never depend on the cache; VITSSL_GRAPH=0 disables it. Counters
  * for tests and bench.py: graphs captured / calls served by a replay since the library was loaded. */
 int vitssl_graph_stats(int64_t* captured, int64_t* replayed);
+/* Switch the replay off (0) / on (1) at run time. The data-parallel module switches it off: buffers
+ * that a collective touches on another stream are released at timing-dependent moments, so the
+ * caller's addresses do not repeat from step to step there and every capture would be wasted. */
+int vitssl_graph_enable(int on);
 
 /* ---- weight casts, EMA, bias gradients (host_* arguments are HOST arrays of device pointers) */
 /* fp32 -> bf16 for `count` tensors in one or a few launches (parameters stay fp32 nn.Parameters;

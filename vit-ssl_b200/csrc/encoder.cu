@@ -191,6 +191,7 @@ static int stack_bwd_body(const vitssl_encoder_bwd_args* a, cudaStream_t stream)
 // one-thread kernel sets ahead of the replay, in stream order. A key that misses takes the direct
 // path, so results never depend on the cache. VITSSL_GRAPH=0 disables; profiling bypasses it.
 // ------------------------------------------------------------------------------------------
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -213,9 +214,10 @@ long long g_graph_captured = 0, g_graph_replayed = 0;
 constexpr size_t GRAPH_CACHE_ENTRIES = 24;
 thread_local const unsigned long long* tl_seed_slot = nullptr;
 
+std::atomic<bool> g_graph_user_on{true};  // vitssl_graph_enable()
 bool graphs_enabled() {
   static const bool on = !(getenv("VITSSL_GRAPH") && atoi(getenv("VITSSL_GRAPH")) == 0);
-  return on;
+  return on && g_graph_user_on.load(std::memory_order_relaxed);
 }
 const unsigned long long* seed_word_address() {
   static const unsigned long long* addr = [] {
@@ -357,6 +359,11 @@ extern "C" int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* a, cudaSt
   key_bwd(key, a);
   return graph_dispatch(key, a->fwd->seed, a->fwd->dropout_p > 0.f, stream,
                         [&](cudaStream_t st) { return stack_bwd_body(a, st); });
+}
+
+extern "C" int vitssl_graph_enable(int on) {
+  g_graph_user_on.store(on != 0);
+  return 0;
 }
 
 extern "C" int vitssl_graph_stats(int64_t* captured, int64_t* replayed) {

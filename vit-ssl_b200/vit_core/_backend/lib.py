@@ -68,6 +68,7 @@ SIGNATURES["vitssl_l1_loss_bwd"] = "pppl" + "s"
 SIGNATURES["vitssl_adamw_step"] = "ppppppp" + "i" + "fffff" + "pp" + "s"
 SIGNATURES["vitssl_profile_read"] = "lplpp"
 SIGNATURES["vitssl_graph_stats"] = "pp"
+SIGNATURES["vitssl_graph_enable"] = "i"
 SIGNATURES["vitssl_multi_ema_shadow"] = "ppppifs"
 SIGNATURES["vitssl_mean_tokens_f32"] = "pp" + "lll" + "s"
 SIGNATURES["vitssl_knn_cosine"] = "pppppppp" + "lllll" + "s"
@@ -173,6 +174,10 @@ def graph_stats():
     c, r = ctypes.c_int64(), ctypes.c_int64()
     call("vitssl_graph_stats", ctypes.addressof(c), ctypes.addressof(r))
     return int(c.value), int(r.value)
+
+
+def graph_enable(on: bool) -> None:
+    call("vitssl_graph_enable", 1 if on else 0)
 
 
 def launch_count(reset: bool = False) -> int:
