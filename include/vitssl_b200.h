@@ -203,7 +203,9 @@ int vitssl_encoder_stack_bwd(const vitssl_encoder_bwd_args* args, vitssl_stream_
 /* Both stack calls replay a CUDA graph of their own launch sequence when they are called again with
  * identical arguments (every scalar and pointer; the dropout seed is exempt: it travels through a
  * device word) — the steady state of a training loop. A call whose arguments were not seen before
- * takes the direct path, so results never depend on the cache; VITSSL_GRAPH=0 disables it. Counters
+ * takes the direct path, so results never depend on the cache; VITSSL_GRAPH=0 disables it. The seed
+ * word is set in stream order, so concurrent stack calls on DIFFERENT streams with dropout must switch
+ * the replay off (vitssl_graph_enable). Counters
  * for tests and bench.py: graphs captured / calls served by a replay since the library was loaded. */
 int vitssl_graph_stats(int64_t* captured, int64_t* replayed);
 /* Switch the replay off (0) / on (1) at run time. The data-parallel module switches it off: buffers
