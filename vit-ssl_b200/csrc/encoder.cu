@@ -296,6 +296,12 @@ int graph_dispatch(std::vector<unsigned char>& key, unsigned long long seed, boo
     lock.unlock();
     return body(stream);
   }
+  if (e->exec == nullptr && g_graph_captured >= 48 && g_graph_replayed < 2 * g_graph_captured) {
+    // the caller's buffer addresses do not repeat (captures are not being reused): stop paying for them
+    g_graph_user_on.store(false);
+    lock.unlock();
+    return body(stream);
+  }
   if (e->exec == nullptr) {
     // capture the same sequencing code; the dropout kernels read the seed word instead of their argument
     if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
